@@ -1,0 +1,227 @@
+"""GCondBase: the shared machinery of GCond / GCondX on the B200 path.
+
+Host-side mirror of graphslim/condensation/gcond_base.py (same constructor contract, same attributes the
+callers touch: ``feat_syn, pge, adj_syn, labels_syn, num_class_dict, syn_class_indices, nnodes_syn``), with the
+per-class matching loop (:156-241) replaced by the batched closed form in ``graphslim_b200.engine``.
+"""
+import os
+import time
+from collections import Counter
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from .. import engine as _engine
+from ..ops import CudaOps, Csr
+from ..pge import PGE
+from ..sampler import ClassSampler
+
+
+def _kernels(device, args):
+    """The only compute backend: CUDA kernels from libgraphslim_b200.so (raises on CPU / missing library)."""
+    return CudaOps(device, precision=int(getattr(args, "gemm_precision", 0)))
+
+
+class _Adam:
+    """torch.optim.Adam(params, lr) with default betas/eps, one fused kernel per tensor (gcond_base.py:68-69)."""
+
+    def __init__(self, K, params, lr):
+        self.K, self.params, self.lr = K, params, float(lr)
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        self.t = 0
+
+    def step(self, grads):
+        self.t += 1
+        for p, g, m, v in zip(self.params, grads, self.m, self.v):
+            if g is None:
+                continue
+            self.K.adam_step(p, g.contiguous().view_as(p), m, v, self.t, self.lr)
+
+
+class GCondBase:
+    def __init__(self, setting, data, args, **kwargs):
+        self.data, self.args, self.setting = data, args, setting
+        self.device = args.device
+        self.K = K = _kernels(self.device, args)
+        if args.with_bn or args.dropout != 0 or getattr(args, "multi_label", False) or getattr(args, "soft_label", 0):
+            raise NotImplementedError("the B200 GCond path covers with_bn=False, dropout=0, hard single labels "
+                                      "(every GCond/GCondX JSON config of the reference)")
+        self.labels_syn = self.data.labels_syn = self.generate_labels_syn(data)
+        n = self.nnodes_syn = self.data.labels_syn.shape[0]
+        self.d = d = data.feat_train.shape[1]
+        print(f'target reduced size:{int(data.feat_train.shape[0] * args.reduction_rate)}')
+        print(f'actual reduced size:{n}')
+        self.feat_syn = torch.empty(n, d, dtype=torch.float32, device=K.device)
+        self.pge = PGE(K, nfeat=d, nnodes=n, args=args)
+        self.adj_syn = None
+        self.optimizer_feat = _Adam(K, [self.feat_syn], args.lr_feat)
+        self.optimizer_pge = _Adam(K, self.pge.parameters(), args.lr_adj)
+        print('adj_syn:', (n, n), 'feat_syn:', self.feat_syn.shape)
+        self.trace = None          # optional callback(kind, **payload) used by the parity tests
+
+    # ------------------------------------------------------------------ gcond_base.py:79-115
+    def generate_labels_syn(self, data):
+        counter = Counter(data.labels_train.tolist())
+        num_class_dict = {}
+        n = len(data.labels_train)
+        ordered = sorted(counter.items(), key=lambda kv: kv[1])     # stable: ties keep first-seen order
+        used, labels_syn = 0, []
+        self.syn_class_indices = {}
+        for ix, (c, num) in enumerate(ordered):
+            if ix == len(ordered) - 1:
+                num_class_dict[c] = max(int(n * self.args.reduction_rate) - used, 1)
+            else:
+                num_class_dict[c] = max(int(num * self.args.reduction_rate), 1)
+                used += num_class_dict[c]
+            self.syn_class_indices[c] = [len(labels_syn), len(labels_syn) + num_class_dict[c]]
+            labels_syn += [c] * num_class_dict[c]
+        self.data.num_class_dict = self.num_class_dict = num_class_dict
+        if self.args.verbose:
+            print(num_class_dict)
+        return np.array(labels_syn)
+
+    # ------------------------------------------------------------------ gcond_base.py:117-151 (init='random')
+    def init(self, with_adj=False):
+        """Random.select (sparsification/random.py:9-17) + MFCoreSet.reduce (model_free_coreset_base.py:16-61)."""
+        args, data = self.args, self.data
+        if args.init != "random":
+            raise NotImplementedError("init reducers other than 'random' are outside the GCond hot path")
+        lt = np.asarray(data.labels_train)
+        base = np.arange(len(data.idx_train)) if args.setting == "ind" else np.asarray(data.idx_train)
+        picks = [np.random.permutation(base[lt == c])[:cnt] for c, cnt in self.num_class_dict.items()]
+        idx = np.hstack(picks)
+        self.init_ids = idx
+        src_feat = data.feat_full if args.setting == "trans" else data.feat_train
+        src_adj = data.adj_full if args.setting == "trans" else data.adj_train
+        src_lab = data.labels_full if args.setting == "trans" else data.labels_train
+        data.adj_syn = torch.from_numpy(np.asarray(src_adj[np.ix_(idx, idx)].todense())).float()
+        data.feat_syn = torch.as_tensor(src_feat)[torch.from_numpy(idx)].float()
+        data.labels_syn = torch.as_tensor(src_lab)[torch.from_numpy(idx)].long()
+        if getattr(args, "save_init", True):
+            from ..dataset_utils import save_reduced
+            keep = args.method
+            args.method = args.init
+            try:
+                save_reduced(data.adj_syn, data.feat_syn, data.labels_syn, args)
+            finally:
+                args.method = keep
+        return (data.feat_syn, data.adj_syn) if with_adj else data.feat_syn
+
+    # ------------------------------------------------------------------ real graph in HBM
+    def _prepare_real(self):
+        """to_tensor + normalize_adj_tensor(sparse=True) (utils.py:220-247,403-413,451-458) and the class lists of
+        retrieve_class_sampler (loader.py:188-195)."""
+        args, data, K = self.args, self.data, self.K
+        if args.setting == 'trans':
+            feats, adj, labels = data.feat_full, data.adj_full, data.labels_full
+        else:
+            feats, adj, labels = data.feat_train, data.adj_train, data.labels_train
+        a = sp.csr_matrix(adj, dtype=np.float32)
+        a = (a + sp.eye(a.shape[0], dtype=np.float32, format="csr")).tocsr()   # A + I; existing diagonal entries sum
+        a.sum_duplicates()
+        a.sort_indices()
+        n = a.shape[0]
+        # degrees and D^-1/2 in float64 on the host (n values), the nnz-sized products on the device
+        rowsum = np.asarray(a.astype(np.float64).sum(1)).ravel()
+        with np.errstate(divide="ignore"):
+            r = np.power(rowsum, -0.5)
+        r[np.isinf(r)] = 0.0
+        rowptr = torch.from_numpy(a.indptr.astype(np.int32)).to(K.device)
+        col = torch.from_numpy(a.indices.astype(np.int32)).to(K.device)
+        raw = torch.from_numpy(a.data.astype(np.float32)).to(K.device)
+        val = K.csr_gcn_norm(rowptr, col, raw, torch.from_numpy(r).to(K.device))
+        # the reference keeps the CSR of the transpose (SparseTensor(...).t()); identical for a symmetric graph
+        at = a.T.tocsr()
+        at.sort_indices()
+        symmetric = (at.indptr.shape == a.indptr.shape and np.array_equal(at.indptr, a.indptr)
+                     and np.array_equal(at.indices, a.indices) and np.array_equal(at.data, a.data))
+        val_host = val.cpu().numpy()
+        if not symmetric:
+            m = sp.csr_matrix((val_host, a.indices, a.indptr), shape=a.shape).T.tocsr()
+            m.sort_indices()
+            a_indptr, a_indices, val_host = m.indptr, m.indices, m.data.astype(np.float32)
+            rowptr = torch.from_numpy(a_indptr.astype(np.int32)).to(K.device)
+            col = torch.from_numpy(a_indices.astype(np.int32)).to(K.device)
+            val = torch.from_numpy(val_host).to(K.device)
+        else:
+            a_indptr, a_indices = a.indptr, a.indices
+        self.adj_csr = Csr(rowptr, col, val, n, n)
+        self.adj_host = (a_indptr.astype(np.int64), a_indices.astype(np.int32), val_host)
+        # features, padded to a 32-byte multiple per row so feature-row gathers are float4 aligned
+        d = feats.shape[1]
+        ld = (d + 7) // 8 * 8
+        fx = torch.zeros(n, ld, dtype=torch.float32, device=K.device)
+        fx[:, :d] = torch.as_tensor(feats).float().to(K.device)
+        self.features = fx[:, :d]
+        self.ones_full = torch.ones(n, 1, dtype=torch.float32, device=K.device)
+        lab = np.asarray(labels).astype(np.int32)
+        lt = np.asarray(data.labels_train)
+        members = []
+        for c in range(data.nclass):
+            members.append(np.asarray(data.idx_train)[lt == c] if args.setting == 'trans'
+                           else np.arange(len(lt))[lt == c])
+        self.sampler = ClassSampler(*self.adj_host, members, args.dataset, args.nlayers, K.device)
+        self.sampler.set_labels(lab)
+        if self.trace:
+            self.trace("norm", rowptr=a_indptr, col=a_indices, val=val_host)
+
+    # ------------------------------------------------------------------ one matching step (gcond_base.py:156-241)
+    def match_step(self, model, materialise=None):
+        """Returns (loss device scalar, dX, dA_hat) for the current feat_syn / adj_syn / model weights."""
+        K = self.K
+        rb = self.sampler.sample(materialise)
+        if self.trace:
+            self.trace("sample", rb=rb)
+        gr = model.real_grads(rb, self.features, self.ones_full)
+        model.syn_forward(self.feat_syn, self.adj_syn)
+        gs = model.syn_grads()
+        loss = K.zeros(1)
+        coeff = model.lay.coeff
+        if materialise is not None:
+            coeff = coeff * torch.as_tensor(np.asarray(materialise, dtype=np.float32), device=K.device)
+        G = K.match(gs, gr, model.widths, model.is_bias, coeff, self.args.dis_metric, loss)
+        dX, dA = model.syn_backward(G, need_dA=not model.identity_adj)
+        return loss, dX, dA, rb
+
+    def draw_model_weights(self, model):
+        """reset_parameters of MyLinear / GraphConvolution (layers.py:30-34,369-373): weight and bias
+        U(-1/sqrt(in), 1/sqrt(in)), drawn with torch's CPU generator in parameter order."""
+        W = []
+        shapes = model.param_shapes
+        for i in range(0, len(shapes), 2):
+            fin, fout = shapes[i]
+            s = 1.0 / np.sqrt(fin)
+            w = torch.empty(fin, fout).uniform_(-s, s)
+            b = torch.zeros(fout).uniform_(-s, s)
+            W += [w, b]
+        return W
+
+    def get_loops(self, args):
+        return args.outer_loop, args.inner_loop
+
+    def check_bn(self, model):
+        return model          # with_bn is rejected in __init__ (gcond_base.py:261-285 is a no-op without BN)
+
+    # ------------------------------------------------------------------ checkpoint hook (gcond_base.py:287-324)
+    def intermediate_evaluation(self, best_val, loss_avg=None, save=True):
+        """The reference trains an evaluation GCN here (SURVEY section 8f, next scope).  An evaluator can be plugged
+        in as ``args.evaluator(data, args) -> (val, test)``; without one the condensed graph is saved as is."""
+        from ..dataset_utils import save_reduced
+        data, args = self.data, self.args
+        if args.verbose:
+            print('loss_avg: {}'.format(loss_avg))
+        evaluator = getattr(args, "evaluator", None)
+        if evaluator is None:
+            if save:
+                save_reduced(data.adj_syn, data.feat_syn, data.labels_syn, args)
+            return best_val
+        res = np.array([evaluator(data, args) for _ in range(args.run_inter_eval)]).T
+        current_val = res[0].mean()
+        args.logger.info('\nVal:  {:.4f} +/- {:.4f}'.format(100 * current_val, 100 * res[0].std()))
+        args.logger.info('Test: {:.4f} +/- {:.4f}'.format(100 * res[1].mean(), 100 * res[1].std()))
+        if save and current_val > best_val:
+            best_val = current_val
+            save_reduced(data.adj_syn, data.feat_syn, data.labels_syn, args)
+        return best_val

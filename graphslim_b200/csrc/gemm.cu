@@ -1,0 +1,205 @@
+// Dense fp32 contractions, SIMT path (exact fp32 FMA).
+//
+//   C = alpha * op(A) * op(B) + beta * C          (row-major, explicit leading dimensions)
+//
+// These replace the ATen matmuls of the condense model and PGE (graphslim/models/sgc.py:39,49,
+// models/layers.py:40-46,377, models/parametrized_adj.py:57-71) and every product autograd
+// derives from them.  The large synthetic-side products are routed to the tcgen05 kernels in
+// gemm_tc.cu when `precision` asks for it; this file is the exact-fp32 path and handles all the
+// small / oddly shaped products (bias outer products, class-segmented weight gradients).
+#include "common.cuh"
+
+namespace gs {
+
+int gemm_tc_dispatch(int ta, int tb, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B,
+                     int64_t ldb, float beta, float* C, int64_t ldc, int precision, cudaStream_t st);
+
+struct GemmProblem {
+  int ta, tb;
+  int M, N, K;
+  float alpha, beta;
+  const float* A;
+  int64_t lda;
+  const float* B;
+  int64_t ldb;
+  float* C;
+  int64_t ldc;
+  // split-K (groups == nullptr): blockIdx.z owns K range [z*kchunk, min(K,(z+1)*kchunk)), atomics when splits > 1
+  int splits, kchunk;
+  // grouped TN (seg != nullptr): blockIdx.z = group g; rows seg[g]..seg[g+1] are the K range,
+  // output column block out_block[g]
+  const int32_t* seg;
+  const int32_t* out_block;
+};
+
+template <int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_simt_kernel(GemmProblem p) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+  const float* A = p.A;
+  const float* B = p.B;
+  float* C = p.C;
+  int kbeg = 0, kend = p.K;
+  bool atomic = false;
+  if (p.seg) {
+    const int g = blockIdx.z;
+    const int r0 = p.seg[g], r1 = p.seg[g + 1];
+    A += (int64_t)r0 * p.lda;  // ta == 1: A is (K x M)
+    B += (int64_t)r0 * p.ldb;  // tb == 0: B is (K x N)
+    C += (int64_t)p.out_block[g] * p.N;
+    kend = r1 - r0;
+  } else if (p.splits > 1) {
+    kbeg = blockIdx.z * p.kchunk;
+    kend = min(p.K, kbeg + p.kchunk);
+    atomic = true;
+  }
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    // ---- stage A tile (BM x BK) as As[k][m]
+    if (p.ta) {
+      for (int i = tid; i < BM * BK; i += NT) {
+        const int m = i % BM, k = i / BM;
+        const int gm = m0 + m, gk = k0 + k;
+        As[k][m] = (gm < p.M && gk < kend) ? __ldg(A + (int64_t)gk * p.lda + gm) : 0.f;
+      }
+    } else {
+      for (int i = tid; i < BM * BK; i += NT) {
+        const int k = i % BK, m = i / BK;
+        const int gm = m0 + m, gk = k0 + k;
+        As[k][m] = (gm < p.M && gk < kend) ? __ldg(A + (int64_t)gm * p.lda + gk) : 0.f;
+      }
+    }
+    // ---- stage B tile (BK x BN) as Bs[k][n]
+    if (p.tb) {
+      for (int i = tid; i < BN * BK; i += NT) {
+        const int k = i % BK, n = i / BK;
+        const int gn = n0 + n, gk = k0 + k;
+        Bs[k][n] = (gn < p.N && gk < kend) ? __ldg(B + (int64_t)gn * p.ldb + gk) : 0.f;
+      }
+    } else {
+      for (int i = tid; i < BN * BK; i += NT) {
+        const int n = i % BN, k = i / BN;
+        const int gn = n0 + n, gk = k0 + k;
+        Bs[k][n] = (gn < p.N && gk < kend) ? __ldg(B + (int64_t)gk * p.ldb + gn) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
+    if (gm >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx * TN + j;
+      if (gn >= p.N) continue;
+      float* c = C + (int64_t)gm * p.ldc + gn;
+      const float v = p.alpha * acc[i][j];
+      if (atomic) {
+        atomicAdd(c, v);
+      } else if (p.beta == 0.f) {
+        *c = v;
+      } else {
+        *c = fmaf(p.beta, *c, v);
+      }
+    }
+  }
+}
+
+__global__ void scale_matrix_kernel(int M, int N, float* C, int64_t ldc, float beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  float* c = C + (i / N) * ldc + (i % N);
+  *c = (beta == 0.f) ? 0.f : *c * beta;
+}
+
+static int launch_simt(GemmProblem& p, int gz, cudaStream_t st) {
+  const bool big = (int64_t)p.M * p.N >= (int64_t)512 * 512 && p.M >= 128 && p.N >= 128;
+  if (big) {
+    dim3 grid((p.N + 127) / 128, (p.M + 127) / 128, gz);
+    gemm_simt_kernel<128, 128, 8, 8, 8><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, gz);
+    gemm_simt_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(p);
+  }
+  return finish_launch("gemm_simt");
+}
+
+}  // namespace gs
+
+extern "C" {
+
+int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
+                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* stream) {
+  GS_REQUIRE(M >= 0 && N >= 0 && K >= 0 && C && ldc >= N);
+  GS_REQUIRE(K == 0 || (A && B));
+  GS_REQUIRE(K == 0 || lda >= (ta ? M : K));
+  GS_REQUIRE(K == 0 || ldb >= (tb ? K : N));
+  if (M == 0 || N == 0) return GS_OK;
+  cudaStream_t st = gs::as_stream(stream);
+  if (precision != 0) {
+    const int rc = gs::gemm_tc_dispatch(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, precision, st);
+    if (rc != GS_ENOSYS) return rc;  // GS_ENOSYS: shape not covered by the tensor-core kernels
+  }
+  gs::GemmProblem p{ta, tb, M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, 1, K, nullptr, nullptr};
+  // split K when the output alone cannot fill the machine (e.g. dW = dY^T H with K = N'^2)
+  const int64_t tiles = (int64_t)((M + 63) / 64) * ((N + 63) / 64);
+  int splits = 1;
+  if (K >= 2048 && tiles < 2 * gs::kNumSMs) {
+    splits = (int)((2 * gs::kNumSMs + tiles - 1) / tiles);
+    const int max_splits = (K + 511) / 512;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1) {
+    int kchunk = (K + splits - 1) / splits;
+    kchunk = (kchunk + 15) / 16 * 16;
+    splits = (K + kchunk - 1) / kchunk;
+    p.splits = splits;
+    p.kchunk = kchunk;
+    if (splits > 1) {
+      const int64_t n = (int64_t)M * N;
+      gs::scale_matrix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(M, N, C, ldc, beta);
+      const int rc = gs::finish_launch("scale_matrix");
+      if (rc) return rc;
+    }
+  }
+  return gs::launch_simt(p, p.splits, st);
+}
+
+int gs_gemm_grouped_tn_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t M, int32_t N,
+                           const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                           void* stream) {
+  GS_REQUIRE(G >= 0 && seg && out_block && M >= 0 && N >= 0 && A && B && C && lda >= M && ldb >= N);
+  if (G == 0 || M == 0 || N == 0) return GS_OK;
+  gs::GemmProblem p{1, 0, M, N, 0, 1.f, 0.f, A, lda, B, ldb, C, ldc, 1, 0, seg, out_block};
+  return gs::launch_simt(p, G, gs::as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// K1/K2/K3: CSR SpMM propagation over the real graph (full graph and sampled blocks).
+//
+//   Y[r,:] (+)= sum_e val[e] * X[col[e],:]
+//
+// Replaces torch_sparse.matmul at graphslim/models/sgc.py:47,51 and models/layers.py:41; with
+// global column ids it also performs the features[n_id] gather of condensation/gcond_base.py:214.
+//
+// Mapping (HBM/L2-bound integer+fp32 gather work, no tensor cores):
+//   * one warp per work item (a row, or a bounded slice of a long row for power-law tails);
+//   * the warp stages 32 (col,val) pairs at a time in shared memory with one coalesced load,
+//     then walks them; every lane owns NV float4 columns of the feature row, so a feature-row
+//     gather is one fully coalesced 512 B * NV request per non-zero (rows are padded to 32 B);
+//   * narrow widths (F/4 < 32, e.g. the class-width propagations of SGC) split the warp into
+//     groups that take alternate non-zeros and are combined with warp shuffles.
+#include "common.cuh"
+
+namespace gs {
+
+constexpr int kWarpsPerBlock = 8;
+
+template <int VEC>
+struct V;
+template <>
+struct V<4> {
+  using T = float4;
+  static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ T ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ T ldrw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st(float* p, T v) { *reinterpret_cast<float4*>(p) = v; }
+  static __device__ __forceinline__ void fma(T& a, float s, T x) {
+    a.x = fmaf(s, x.x, a.x);
+    a.y = fmaf(s, x.y, a.y);
+    a.z = fmaf(s, x.z, a.z);
+    a.w = fmaf(s, x.w, a.w);
+  }
+  static __device__ __forceinline__ T add(T a, T b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+  static __device__ __forceinline__ T shfl_xor(T a, int o) {
+    return make_float4(__shfl_xor_sync(0xffffffffu, a.x, o), __shfl_xor_sync(0xffffffffu, a.y, o),
+                       __shfl_xor_sync(0xffffffffu, a.z, o), __shfl_xor_sync(0xffffffffu, a.w, o));
+  }
+  static __device__ __forceinline__ void atomic_add(float* p, T v) {
+    atomicAdd(reinterpret_cast<float4*>(p), v);
+  }
+};
+template <>
+struct V<1> {
+  using T = float;
+  static __device__ __forceinline__ T zero() { return 0.f; }
+  static __device__ __forceinline__ T ld(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ T ldrw(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, T v) { *p = v; }
+  static __device__ __forceinline__ void fma(T& a, float s, T x) { a = fmaf(s, x, a); }
+  static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+  static __device__ __forceinline__ T shfl_xor(T a, int o) { return __shfl_xor_sync(0xffffffffu, a, o); }
+  static __device__ __forceinline__ void atomic_add(float* p, T v) { atomicAdd(p, v); }
+};
+
+struct Items {
+  int32_t n_items;
+  const int32_t* rowptr;
+  const int32_t* chunk_row;
+  const int32_t* chunk_beg;
+  const int32_t* chunk_end;
+};
+
+__device__ __forceinline__ void item_range(const Items& it, int i, int& row, int& beg, int& end) {
+  if (it.chunk_row) {
+    row = it.chunk_row[i];
+    beg = it.chunk_beg[i];
+    end = it.chunk_end[i];
+  } else {
+    row = i;
+    beg = it.rowptr[i];
+    end = it.rowptr[i + 1];
+  }
+}
+
+// Wide rows: L = ceil(F/VEC) >= 32 vector columns, tiled by 32*NV per warp (blockIdx.y = column tile).
+template <int VEC, int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+spmm_wide_kernel(Items it, const int32_t* __restrict__ col, const float* __restrict__ val,
+                 const float* __restrict__ X, int64_t ldx, int L, float* __restrict__ Y, int64_t ldy, int mode) {
+  using VT = typename V<VEC>::T;
+  __shared__ int32_t s_col[kWarpsPerBlock][32];
+  __shared__ float s_val[kWarpsPerBlock][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kWarpsPerBlock + warp;
+  if (item >= it.n_items) return;
+  int row, beg, end;
+  item_range(it, item, row, beg, end);
+  const int tile0 = blockIdx.y * (32 * NV);  // first vector column of this tile
+  VT acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = V<VEC>::zero();
+  bool live[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) live[v] = (tile0 + v * 32 + lane) < L;
+
+  for (int base = beg; base < end; base += 32) {
+    const int cnt = min(32, end - base);
+    __syncwarp();
+    if (lane < cnt) {
+      s_col[warp][lane] = __ldg(col + base + lane);
+      s_val[warp][lane] = __ldg(val + base + lane);
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const float a = s_val[warp][j];
+      const float* xr = X + (int64_t)s_col[warp][j] * ldx + (int64_t)(tile0 + lane) * VEC;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (live[v]) V<VEC>::fma(acc[v], a, V<VEC>::ld(xr + (int64_t)v * 32 * VEC));
+      }
+    }
+  }
+  float* yr = Y + (int64_t)row * ldy + (int64_t)(tile0 + lane) * VEC;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    if (!live[v]) continue;
+    float* p = yr + (int64_t)v * 32 * VEC;
+    if (mode == 2) {
+      V<VEC>::atomic_add(p, acc[v]);
+    } else if (mode == 1) {
+      V<VEC>::st(p, V<VEC>::add(V<VEC>::ldrw(p), acc[v]));
+    } else {
+      V<VEC>::st(p, acc[v]);
+    }
+  }
+}
+
+// Narrow rows: L < 32.  LPG (power of two >= L) lanes cover the width, 32/LPG groups split the non-zeros.
+template <int VEC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+spmm_narrow_kernel(Items it, const int32_t* __restrict__ col, const float* __restrict__ val,
+                   const float* __restrict__ X, int64_t ldx, int L, int LPG, float* __restrict__ Y, int64_t ldy,
+                   int mode) {
+  using VT = typename V<VEC>::T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kWarpsPerBlock + warp;
+  if (item >= it.n_items) return;
+  int row, beg, end;
+  item_range(it, item, row, beg, end);
+  const int G = 32 / LPG;
+  const int g = lane / LPG, l = lane % LPG;
+  const bool live = l < L;
+  VT acc = V<VEC>::zero();
+  for (int e = beg + g; e < end; e += G) {
+    const float a = __ldg(val + e);
+    const int32_t c = __ldg(col + e);
+    if (live) V<VEC>::fma(acc, a, V<VEC>::ld(X + (int64_t)c * ldx + (int64_t)l * VEC));
+  }
+  for (int o = LPG; o < 32; o <<= 1) acc = V<VEC>::add(acc, V<VEC>::shfl_xor(acc, o));
+  if (g == 0 && live) {
+    float* p = Y + (int64_t)row * ldy + (int64_t)l * VEC;
+    if (mode == 2) {
+      V<VEC>::atomic_add(p, acc);
+    } else if (mode == 1) {
+      V<VEC>::st(p, V<VEC>::add(V<VEC>::ldrw(p), acc));
+    } else {
+      V<VEC>::st(p, acc);
+    }
+  }
+}
+
+template <int VEC>
+static int launch_spmm(const Items& it, const int32_t* col, const float* val, const float* X, int64_t ldx, int F,
+                       float* Y, int64_t ldy, int mode, cudaStream_t st) {
+  const int L = (F + VEC - 1) / VEC;
+  const int gx = (it.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (gx == 0) return GS_OK;
+  if (L < 32) {
+    int LPG = 1;
+    while (LPG < L) LPG <<= 1;
+    spmm_narrow_kernel<VEC><<<gx, kWarpsPerBlock * 32, 0, st>>>(it, col, val, X, ldx, L, LPG, Y, ldy, mode);
+    return finish_launch("spmm_narrow");
+  }
+  const int ntiles = (L + 255) / 256;
+  const int per_tile = (L + ntiles - 1) / ntiles;
+  const int nv = (per_tile + 31) / 32;
+  dim3 grid(gx, (L + 32 * nv - 1) / (32 * nv));
+#define GS_SPMM_CASE(NVV)                                                                                        \
+  case NVV:                                                                                                      \
+    spmm_wide_kernel<VEC, NVV><<<grid, kWarpsPerBlock * 32, 0, st>>>(it, col, val, X, ldx, L, Y, ldy, mode);     \
+    break;
+  switch (nv) {
+    GS_SPMM_CASE(1)
+    GS_SPMM_CASE(2)
+    GS_SPMM_CASE(3)
+    GS_SPMM_CASE(4)
+    GS_SPMM_CASE(5)
+    GS_SPMM_CASE(6)
+    GS_SPMM_CASE(7)
+    GS_SPMM_CASE(8)
+    default:
+      return GS_EINVAL;
+  }
+#undef GS_SPMM_CASE
+  return finish_launch("spmm_wide");
+}
+
+static inline bool vec4_ok(const float* X, int64_t ldx, const float* Y, int64_t ldy, int F) {
+  return (F % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
+         ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// scatter form (transpose-free backward through a rectangular block)
+template <int VEC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+spmm_scatter_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                    const float* __restrict__ val, const float* __restrict__ dY, int64_t ldy, int L,
+                    float* __restrict__ dX, int64_t ldx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kWarpsPerBlock + warp;
+  if (row >= n_rows) return;
+  const int beg = rowptr[row], end = rowptr[row + 1];
+  for (int l = lane; l < L; l += 32) {
+    const typename V<VEC>::T g = V<VEC>::ld(dY + (int64_t)row * ldy + (int64_t)l * VEC);
+    for (int e = beg; e < end; ++e) {
+      typename V<VEC>::T c = V<VEC>::zero();
+      V<VEC>::fma(c, __ldg(val + e), g);
+      V<VEC>::atomic_add(dX + (int64_t)__ldg(col + e) * ldx + (int64_t)l * VEC, c);
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+gather_rows_kernel(int n, const int32_t* __restrict__ idx, const float* __restrict__ X, int64_t ldx, int L,
+                   float* __restrict__ out, int64_t ldo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kWarpsPerBlock + warp;
+  if (r >= n) return;
+  const float* src = X + (int64_t)__ldg(idx + r) * ldx;
+  float* dst = out + (int64_t)r * ldo;
+  for (int l = lane; l < L; l += 32) V<VEC>::st(dst + (int64_t)l * VEC, V<VEC>::ld(src + (int64_t)l * VEC));
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+csr_gcn_norm_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                    const float* __restrict__ a, const double* __restrict__ r, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kWarpsPerBlock + warp;
+  if (row >= n_rows) return;
+  const double ri = r[row];
+  for (int e = rowptr[row] + lane; e < rowptr[row + 1]; e += 32) {
+    // (D^-1/2 A) D^-1/2 in float64, one rounding to fp32: graphslim/utils.py:451-458 then :664
+    const double left = __dmul_rn(ri, (double)a[e]);
+    out[e] = (float)__dmul_rn(left, r[col[e]]);
+  }
+}
+
+}  // namespace gs
+
+extern "C" {
+
+int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
+                    int64_t ldx, int32_t F, float* Y, int64_t ldy, int accumulate, int32_t n_chunks,
+                    const int32_t* chunk_row, const int32_t* chunk_beg, const int32_t* chunk_end, void* stream) {
+  GS_REQUIRE(n_rows >= 0 && F > 0 && rowptr && X && Y && ldx >= F && ldy >= F);
+  GS_REQUIRE(n_chunks == 0 || (chunk_row && chunk_beg && chunk_end));
+  if (n_rows == 0) return GS_OK;
+  gs::Items it{n_chunks > 0 ? n_chunks : n_rows, rowptr, n_chunks > 0 ? chunk_row : nullptr, chunk_beg, chunk_end};
+  const int mode = n_chunks > 0 ? 2 : (accumulate ? 1 : 0);
+  cudaStream_t st = gs::as_stream(stream);
+  if (gs::vec4_ok(X, ldx, Y, ldy, F)) return gs::launch_spmm<4>(it, col, val, X, ldx, F, Y, ldy, mode, st);
+  return gs::launch_spmm<1>(it, col, val, X, ldx, F, Y, ldy, mode, st);
+}
+
+int gs_spmm_csr_scatter_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val,
+                            const float* dY, int64_t ldy, int32_t F, float* dX, int64_t ldx, void* stream) {
+  GS_REQUIRE(n_rows >= 0 && F > 0 && rowptr && dY && dX && ldx >= F && ldy >= F);
+  if (n_rows == 0) return GS_OK;
+  const int gx = (n_rows + gs::kWarpsPerBlock - 1) / gs::kWarpsPerBlock;
+  cudaStream_t st = gs::as_stream(stream);
+  if (gs::vec4_ok(dY, ldy, dX, ldx, F)) {
+    gs::spmm_scatter_kernel<4><<<gx, gs::kWarpsPerBlock * 32, 0, st>>>(n_rows, rowptr, col, val, dY, ldy, F / 4, dX, ldx);
+  } else {
+    gs::spmm_scatter_kernel<1><<<gx, gs::kWarpsPerBlock * 32, 0, st>>>(n_rows, rowptr, col, val, dY, ldy, F, dX, ldx);
+  }
+  return gs::finish_launch("spmm_scatter");
+}
+
+int gs_gather_rows_f32(int32_t n, const int32_t* idx, const float* X, int64_t ldx, int32_t F, float* out, int64_t ldo,
+                       void* stream) {
+  GS_REQUIRE(n >= 0 && F > 0 && idx && X && out && ldx >= F && ldo >= F);
+  if (n == 0) return GS_OK;
+  const int gx = (n + gs::kWarpsPerBlock - 1) / gs::kWarpsPerBlock;
+  cudaStream_t st = gs::as_stream(stream);
+  if (gs::vec4_ok(X, ldx, out, ldo, F)) {
+    gs::gather_rows_kernel<4><<<gx, gs::kWarpsPerBlock * 32, 0, st>>>(n, idx, X, ldx, F / 4, out, ldo);
+  } else {
+    gs::gather_rows_kernel<1><<<gx, gs::kWarpsPerBlock * 32, 0, st>>>(n, idx, X, ldx, F, out, ldo);
+  }
+  return gs::finish_launch("gather_rows");
+}
+
+int gs_csr_gcn_norm_f64(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* a, const double* r,
+                        float* val_out, void* stream) {
+  GS_REQUIRE(n_rows >= 0 && rowptr && col && a && r && val_out);
+  if (n_rows == 0) return GS_OK;
+  const int gx = (n_rows + gs::kWarpsPerBlock - 1) / gs::kWarpsPerBlock;
+  gs::csr_gcn_norm_kernel<<<gx, gs::kWarpsPerBlock * 32, 0, gs::as_stream(stream)>>>(n_rows, rowptr, col, a, r, val_out);
+  return gs::finish_launch("csr_gcn_norm");
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+"""Kernel namespace: thin torch-tensor wrappers over the C ABI (one C call per method).
+
+PyTorch only supplies device memory and the stream here.  Every method launches hand-written sm_100a
+kernels from libgraphslim_b200.so on the current CUDA stream; CPU tensors are rejected.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class Csr:
+    """CSR matrix in HBM: int32 rowptr/col, fp32 val."""
+
+    __slots__ = ("rowptr", "col", "val", "n_rows", "n_cols", "chunks")
+
+    def __init__(self, rowptr, col, val, n_rows, n_cols, chunks=None):
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.chunks = chunks      # optional (chunk_row, chunk_beg, chunk_end) int32 tensors for long-row splitting
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _f32(t, name="tensor"):
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA float32 tensor, got {t.dtype} on {t.device}")
+    return t
+
+
+def _mat(t, name):
+    _f32(t, name)
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"{name}: need a 2-D matrix with unit column stride, got shape {tuple(t.shape)} "
+                         f"stride {t.stride()}")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    return max(ld, t.shape[1])
+
+
+METRIC_ID = {"ours": 0, "mse": 1, "cos": 2}
+
+
+class CudaOps:
+    """All device work of the GCond path.  ``precision``: 0 exact fp32 SIMT, 1 tcgen05 3xBF16, 2 tcgen05 BF16."""
+
+    def __init__(self, device, precision=0):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.GraphSlimLibraryError("graphslim_b200 runs on CUDA devices only (no CPU fallback); "
+                                             f"got device {device!r}")
+        self.precision = int(precision)
+
+    # -- plumbing ------------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=torch.float32):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def launches(self):
+        return int(self.lib.gs_launch_count())
+
+    # -- dense ---------------------------------------------------------------------------------
+    def gemm(self, A, B, ta=False, tb=False, out=None, alpha=1.0, beta=0.0, precision=None):
+        lda, ldb = _mat(A, "A"), _mat(B, "B")
+        M, K = (A.shape[1], A.shape[0]) if ta else (A.shape[0], A.shape[1])
+        K2, N = (B.shape[1], B.shape[0]) if tb else (B.shape[0], B.shape[1])
+        if K != K2:
+            raise ValueError(f"gemm inner dimensions differ: {K} vs {K2}")
+        if out is None:
+            if beta != 0.0:
+                raise ValueError("beta != 0 needs an output to accumulate into")
+            out = self.empty(M, N)
+        ldc = _mat(out, "out")
+        if out.shape != (M, N):
+            raise ValueError(f"gemm output shape {tuple(out.shape)} != {(M, N)}")
+        prec = self.precision if precision is None else precision
+        _lib.check(self.lib.gs_gemm_f32(int(ta), int(tb), M, N, K, alpha, _ptr(A), lda, _ptr(B), ldb, beta,
+                                        _ptr(out), ldc, prec, self.stream), "gs_gemm_f32")
+        return out
+
+    def gemm_grouped_tn(self, A, B, seg, out_block, nblk):
+        """out[:, out_block[g]*N:(out_block[g]+1)*N] = A[seg[g]:seg[g+1]]^T @ B[seg[g]:seg[g+1]]; other blocks zero."""
+        lda, ldb = _mat(A, "A"), _mat(B, "B")
+        M, N = A.shape[1], B.shape[1]
+        G = seg.numel() - 1
+        out = self.zeros(M, nblk * N) if G < nblk else self.empty(M, nblk * N)
+        _lib.check(self.lib.gs_gemm_grouped_tn_f32(G, _ptr(seg), _ptr(out_block), M, N, _ptr(A), lda, _ptr(B), ldb,
+                                                   _ptr(out), nblk * N, self.stream), "gs_gemm_grouped_tn_f32")
+        return out
+
+    # -- sparse --------------------------------------------------------------------------------
+    def spmm(self, csr, X, out=None, accumulate=False):
+        ldx = _mat(X, "X")
+        F = X.shape[1]
+        n_chunks, cr, cb, ce = 0, None, None, None
+        if csr.chunks is not None:
+            cr, cb, ce = csr.chunks
+            n_chunks = cr.numel()
+        if out is None:
+            out = self.zeros(csr.n_rows, F) if n_chunks else self.empty(csr.n_rows, F)
+        elif n_chunks and not accumulate:
+            out.zero_()
+        ldy = _mat(out, "out")
+        _lib.check(self.lib.gs_spmm_csr_f32(csr.n_rows, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val), _ptr(X), ldx,
+                                            F, _ptr(out), ldy, int(accumulate), n_chunks, _ptr(cr), _ptr(cb),
+                                            _ptr(ce), self.stream), "gs_spmm_csr_f32")
+        return out
+
+    def spmm_scatter(self, csr, dY, out):
+        """out[col[e],:] += val[e]*dY[row(e),:] (atomics); `out` must be pre-initialised."""
+        ldy, ldx = _mat(dY, "dY"), _mat(out, "out")
+        _lib.check(self.lib.gs_spmm_csr_scatter_f32(csr.n_rows, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val),
+                                                    _ptr(dY), ldy, dY.shape[1], _ptr(out), ldx, self.stream),
+                   "gs_spmm_csr_scatter_f32")
+        return out
+
+    def gather_rows(self, X, idx):
+        ldx = _mat(X, "X")
+        out = self.empty(idx.numel(), X.shape[1])
+        _lib.check(self.lib.gs_gather_rows_f32(idx.numel(), _ptr(idx), _ptr(X), ldx, X.shape[1], _ptr(out),
+                                               X.shape[1], self.stream), "gs_gather_rows_f32")
+        return out
+
+    def csr_gcn_norm(self, rowptr, col, a, r64):
+        out = torch.empty_like(a)
+        _lib.check(self.lib.gs_csr_gcn_norm_f64(rowptr.numel() - 1, _ptr(rowptr), _ptr(col), _ptr(a), _ptr(r64),
+                                                _ptr(out), self.stream), "gs_csr_gcn_norm_f64")
+        return out
+
+    # -- condense-model glue -------------------------------------------------------------------
+    def bias_act(self, Z, bias, relu):
+        ldz = _mat(Z, "Z")
+        _lib.check(self.lib.gs_bias_act_f32(Z.shape[0], Z.shape[1], _ptr(Z), ldz, _ptr(bias), int(relu), self.stream),
+                   "gs_bias_act_f32")
+        return Z
+
+    def relu_mask(self, D, H, groups=1):
+        """D viewed as (rows, groups, cols) is zeroed where H (rows, cols) <= 0; in place."""
+        ldh = _mat(H, "H")
+        rows, cols = H.shape
+        if not D.is_contiguous() or D.numel() != rows * groups * cols:
+            raise ValueError("relu_mask: D must be contiguous with rows*groups*cols elements")
+        _lib.check(self.lib.gs_relu_mask_f32(rows, groups, cols, _ptr(D), _ptr(H), ldh, self.stream),
+                   "gs_relu_mask_f32")
+        return D
+
+    def softmax_residual(self, Z, labels, row_scale, want_nll=False):
+        ldz = _mat(Z, "Z")
+        rows, C = Z.shape
+        S, R = self.empty(rows, C), self.empty(rows, C)
+        nll = self.empty(rows) if want_nll else None
+        _lib.check(self.lib.gs_softmax_residual_f32(rows, C, _ptr(Z), ldz, _ptr(labels), _ptr(row_scale), _ptr(S),
+                                                    _ptr(R), _ptr(nll), self.stream), "gs_softmax_residual_f32")
+        return (S, R, nll) if want_nll else (S, R)
+
+    def expand_class_blocks(self, R, blk, nblk):
+        rows, C = R.shape
+        E = self.empty(rows, nblk * C)
+        _lib.check(self.lib.gs_expand_class_blocks_f32(rows, C, nblk, _ptr(R.contiguous()), _ptr(blk), _ptr(E),
+                                                       self.stream), "gs_expand_class_blocks_f32")
+        return E
+
+    def pick_class_blocks(self, Zf, blk, nblk):
+        rows = Zf.shape[0]
+        C = Zf.shape[1] // nblk
+        Q = self.empty(rows, C)
+        _lib.check(self.lib.gs_pick_class_blocks_f32(rows, C, nblk, _ptr(Zf.contiguous()), _ptr(blk), _ptr(Q),
+                                                     self.stream), "gs_pick_class_blocks_f32")
+        return Q
+
+    def softmax_jvp(self, S, Q, row_scale):
+        rows, C = S.shape
+        dZ = self.empty(rows, C)
+        _lib.check(self.lib.gs_softmax_jvp_f32(rows, C, _ptr(S), _ptr(Q), _ptr(row_scale), _ptr(dZ), self.stream),
+                   "gs_softmax_jvp_f32")
+        return dZ
+
+    # -- gradient matching -----------------------------------------------------------------------
+    def match(self, gs_list, gr_list, widths, is_bias, coeff, metric, loss_accum):
+        """condensation/utils.py:12-106 on class-column gradients.
+
+        gs_list/gr_list: per parameter a (rows x n_class*width) matrix; returns dLoss/dgs in the same
+        layout and adds the loss into the device scalar ``loss_accum``.
+        """
+        n_class = coeff.numel()
+        cols = [g.shape[1] for g in gs_list]
+        off = np.concatenate([[0], np.cumsum(cols)]).astype(np.int32)
+        total = int(off[-1])
+        stats = self.empty(4, total)
+        for p, (a, b) in enumerate(zip(gs_list, gr_list)):
+            ld = _mat(a, "gs")
+            if _mat(b, "gr") != ld:
+                raise ValueError("match: gs/gr leading dimensions differ")
+            _lib.check(self.lib.gs_match_col_stats_f32(a.shape[0], a.shape[1], _ptr(a), _ptr(b), ld,
+                                                       stats.data_ptr() + 4 * int(off[p]), total, self.stream),
+                       "gs_match_col_stats_f32")
+        key = (tuple(cols), tuple(widths), tuple(is_bias))
+        cache = getattr(self, "_match_desc", None)
+        if cache is None or cache[0] != key:
+            dev = lambda x: torch.tensor(np.asarray(x, dtype=np.int32), device=self.device)
+            cache = (key, dev(off), dev(widths), dev([int(b) for b in is_bias]))
+            self._match_desc = cache
+        alpha, beta, closs = self.empty(total), self.empty(total), self.empty(n_class)
+        _lib.check(self.lib.gs_match_finalize_f32(METRIC_ID[metric], len(gs_list), _ptr(cache[1]), _ptr(cache[2]),
+                                                  _ptr(cache[3]), n_class, _ptr(coeff), _ptr(stats), total,
+                                                  _ptr(alpha), _ptr(beta), _ptr(closs), _ptr(loss_accum),
+                                                  self.stream), "gs_match_finalize_f32")
+        out = []
+        for p, (a, b) in enumerate(zip(gs_list, gr_list)):
+            G = torch.empty_like(a)
+            ld = _mat(a, "gs")
+            _lib.check(self.lib.gs_match_apply_f32(a.shape[0], a.shape[1], _ptr(a), _ptr(b), ld,
+                                                   alpha.data_ptr() + 4 * int(off[p]),
+                                                   beta.data_ptr() + 4 * int(off[p]), _ptr(G), self.stream),
+                       "gs_match_apply_f32")
+            out.append(G)
+        return out
+
+    # -- dense normalisation ---------------------------------------------------------------------
+    def dense_gcn_norm(self, A):
+        n = A.shape[0]
+        Ahat, r = self.empty(n, n), self.empty(n)
+        _lib.check(self.lib.gs_dense_gcn_norm_fwd_f32(n, _ptr(A), _ptr(Ahat), _ptr(r), self.stream),
+                   "gs_dense_gcn_norm_fwd_f32")
+        return Ahat, r
+
+    def dense_gcn_norm_bwd(self, dAhat, Ahat, r):
+        n = Ahat.shape[0]
+        dA, work = self.empty(n, n), self.empty(2 * n)
+        _lib.check(self.lib.gs_dense_gcn_norm_bwd_f32(n, _ptr(dAhat), _ptr(Ahat), _ptr(r), _ptr(dA), _ptr(work),
+                                                      self.stream), "gs_dense_gcn_norm_bwd_f32")
+        return dA
+
+    # -- PGE ---------------------------------------------------------------------------------------
+    def _work(self, n):
+        return torch.empty(n, dtype=torch.float64, device=self.device)
+
+    def pge_l1_stats(self, Pa, Pb, chunk_off, eps=1e-5):
+        n, h = Pa.shape
+        nch = chunk_off.numel() - 1
+        mean, rstd = self.empty(nch, h), self.empty(nch, h)
+        _lib.check(self.lib.gs_pge_l1_stats_f32(n, h, _ptr(Pa), _ptr(Pb), nch, _ptr(chunk_off), eps, _ptr(mean),
+                                                _ptr(rstd), _ptr(self._work(2 * nch * h)), self.stream),
+                   "gs_pge_l1_stats_f32")
+        return mean, rstd
+
+    def pge_l1_expand(self, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
+        n, h = Pa.shape
+        H1 = self.empty(n * n, h)
+        _lib.check(self.lib.gs_pge_l1_expand_f32(n, h, _ptr(Pa), _ptr(Pb), chunk_off.numel() - 1, _ptr(chunk_off),
+                                                 _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(H1),
+                                                 self.stream), "gs_pge_l1_expand_f32")
+        return H1
+
+    def col_stats_chunked(self, Y, chunk_off, eps=1e-5):
+        rows, h = Y.shape
+        nch = chunk_off.numel() - 1
+        mean, rstd = self.empty(nch, h), self.empty(nch, h)
+        _lib.check(self.lib.gs_col_stats_chunked_f32(rows, h, _ptr(Y), nch, _ptr(chunk_off), eps, _ptr(mean),
+                                                     _ptr(rstd), _ptr(self._work(2 * nch * h)), self.stream),
+                   "gs_col_stats_chunked_f32")
+        return mean, rstd
+
+    def pge_l3(self, Y2, chunk_off, mean, rstd, gamma, beta, w3, b3):
+        rows, h = Y2.shape
+        E = self.empty(rows)
+        _lib.check(self.lib.gs_pge_l3_f32(rows, h, _ptr(Y2), chunk_off.numel() - 1, _ptr(chunk_off), _ptr(mean),
+                                          _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(w3), _ptr(b3), _ptr(E),
+                                          self.stream), "gs_pge_l3_f32")
+        return E
+
+    def pge_symm_sigmoid(self, E, n):
+        A = self.empty(n, n)
+        _lib.check(self.lib.gs_pge_symm_sigmoid_f32(n, _ptr(E), _ptr(A), self.stream), "gs_pge_symm_sigmoid_f32")
+        return A
+
+    def pge_symm_sigmoid_bwd(self, dA, A):
+        n = A.shape[0]
+        dE = self.empty(n * n)
+        _lib.check(self.lib.gs_pge_symm_sigmoid_bwd_f32(n, _ptr(dA), _ptr(A), _ptr(dE), self.stream),
+                   "gs_pge_symm_sigmoid_bwd_f32")
+        return dE
+
+    def pge_l3_bwd_stats(self, Y2, dE, chunk_off, mean, rstd, gamma, beta, w3):
+        rows, h = Y2.shape
+        nch = chunk_off.numel() - 1
+        s1, s2 = self.empty(nch, h), self.empty(nch, h)
+        dw3, db3 = self.zeros(h), self.zeros(1)
+        _lib.check(self.lib.gs_pge_l3_bwd_stats_f32(rows, h, _ptr(Y2), _ptr(dE), nch, _ptr(chunk_off), _ptr(mean),
+                                                    _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(w3), _ptr(s1), _ptr(s2),
+                                                    _ptr(dw3), _ptr(db3), _ptr(self._work(2 * nch * h + h + 1)),
+                                                    self.stream), "gs_pge_l3_bwd_stats_f32")
+        return s1, s2, dw3, db3
+
+    def pge_bn2_bwd_apply(self, Y2, dE, chunk_off, mean, rstd, gamma, beta, w3, s1, s2):
+        rows, h = Y2.shape
+        dY2 = self.empty(rows, h)
+        _lib.check(self.lib.gs_pge_bn2_bwd_apply_f32(rows, h, _ptr(Y2), _ptr(dE), chunk_off.numel() - 1,
+                                                     _ptr(chunk_off), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta),
+                                                     _ptr(w3), _ptr(s1), _ptr(s2), _ptr(dY2), self.stream),
+                   "gs_pge_bn2_bwd_apply_f32")
+        return dY2
+
+    def pge_bn1_bwd_stats(self, dH1, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
+        n, h = Pa.shape
+        nch = chunk_off.numel() - 1
+        s1, s2 = self.empty(nch, h), self.empty(nch, h)
+        _lib.check(self.lib.gs_pge_bn1_bwd_stats_f32(n, h, _ptr(dH1), _ptr(Pa), _ptr(Pb), nch, _ptr(chunk_off),
+                                                     _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(s1),
+                                                     _ptr(s2), _ptr(self._work(2 * nch * h)), self.stream),
+                   "gs_pge_bn1_bwd_stats_f32")
+        return s1, s2
+
+    def pge_bn1_bwd_reduce(self, dH1, Pa, Pb, chunk_off, mean, rstd, gamma, beta, s1, s2):
+        n, h = Pa.shape
+        dPa, dPb = self.empty(n, h), self.empty(n, h)
+        _lib.check(self.lib.gs_pge_bn1_bwd_reduce_f32(n, h, _ptr(dH1), _ptr(Pa), _ptr(Pb), chunk_off.numel() - 1,
+                                                      _ptr(chunk_off), _ptr(mean), _ptr(rstd), _ptr(gamma),
+                                                      _ptr(beta), _ptr(s1), _ptr(s2), _ptr(dPa), _ptr(dPb),
+                                                      self.stream), "gs_pge_bn1_bwd_reduce_f32")
+        return dPa, dPb
+
+    # -- optimiser ---------------------------------------------------------------------------------
+    def adam_step(self, p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        if not (p.is_contiguous() and g.is_contiguous()):
+            raise ValueError("adam_step needs contiguous tensors")
+        _lib.check(self.lib.gs_adam_step_f32(p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), step, lr, beta1, beta2,
+                                             eps, self.stream), "gs_adam_step_f32")
+
+    def axpby(self, a, x, b, y):
+        _lib.check(self.lib.gs_axpby_f32(y.numel(), a, _ptr(x), b, _ptr(y), self.stream), "gs_axpby_f32")
+        return y

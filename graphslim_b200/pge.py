@@ -1,0 +1,96 @@
+"""PGE: pairwise adjacency generator (graphslim/models/parametrized_adj.py:7-86), forward and backward.
+
+Parameters live as plain device tensors in nn.Linear / BatchNorm1d layout and order so that
+``parameters()`` lines up with the reference's ``pge.parameters()``:
+    layers.0.weight (h,2d), layers.0.bias, layers.1.weight (h,h), layers.1.bias, layers.2.weight (1,h),
+    layers.2.bias, bns.0.weight, bns.0.bias, bns.1.weight, bns.1.bias.
+
+Initial values are drawn with torch's CPU generator in the reference's order (each Linear twice: once in its
+constructor, once more by PGE.reset_parameters, parametrized_adj.py:35,79-86) and copied to HBM, so a run
+is seed-comparable with the reference's gpu_id=-1 path.
+"""
+import numpy as np
+import torch
+
+
+def pge_hidden(dataset, reduction_rate):
+    """parametrized_adj.py:11-17."""
+    nhid = 128
+    if dataset in ("ogbn-arxiv", "arxiv", "flickr"):
+        nhid = 256
+    if dataset in ("reddit",):
+        nhid = 128 if reduction_rate == 0.01 else 256
+    return nhid
+
+
+class PGE:
+    def __init__(self, K, nfeat, nnodes, args):
+        self.K = K
+        self.n, self.d = int(nnodes), int(nfeat)
+        self.h = h = pge_hidden(args.dataset, args.reduction_rate)
+        self.nchunks = 5 if (args.dataset == "reddit" and args.reduction_rate >= 0.01) else 1
+        dims = [(2 * nfeat, h), (h, h), (h, 1)]
+        lins = [torch.nn.Linear(i, o) for i, o in dims]          # first draw (constructor)
+        for lin in lins:                                          # second draw (PGE.reset_parameters)
+            lin.reset_parameters()
+        dev = K.device
+        self.W = [lin.weight.detach().clone().to(dev) for lin in lins]
+        self.b = [lin.bias.detach().clone().to(dev) for lin in lins]
+        self.gamma = [torch.ones(h, device=dev), torch.ones(h, device=dev)]
+        self.beta = [torch.zeros(h, device=dev), torch.zeros(h, device=dev)]
+        # np.array_split boundaries over the n*n pair rows (parametrized_adj.py:43)
+        total = self.n * self.n
+        sizes = [total // self.nchunks + (1 if i < total % self.nchunks else 0) for i in range(self.nchunks)]
+        self.chunk_off = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64, device=dev)
+        self.eps = 1e-5
+
+    def parameters(self):
+        return [self.W[0], self.b[0], self.W[1], self.b[1], self.W[2], self.b[2],
+                self.gamma[0], self.beta[0], self.gamma[1], self.beta[1]]
+
+    # ---------------------------------------------------------------------------------- forward
+    def forward(self, x, keep=True):
+        """adj (n,n) = zero-diag(sigmoid((E+E^T)/2)),  E[i,j] = MLP([x_j, x_i]).  BN always uses batch stats."""
+        K, n, d, h = self.K, self.n, self.d, self.h
+        W1 = self.W[0]
+        Pa = K.gemm(x, W1[:, :d], tb=True)                       # layer 1, first half: indexed by j
+        Pb = K.gemm(x, W1[:, d:], tb=True)                       # second half: indexed by i (bias cancels in BN)
+        mean1, rstd1 = K.pge_l1_stats(Pa, Pb, self.chunk_off, self.eps)
+        H1 = K.pge_l1_expand(Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0])
+        Y2 = K.gemm(H1, self.W[1], tb=True)                      # the N'^2 x h x h product (bias cancels in BN)
+        mean2, rstd2 = K.col_stats_chunked(Y2, self.chunk_off, self.eps)
+        E = K.pge_l3(Y2, self.chunk_off, mean2, rstd2, self.gamma[1], self.beta[1], self.W[2].view(-1), self.b[2])
+        A = K.pge_symm_sigmoid(E, n)
+        if keep:
+            self._saved = (x, Pa, Pb, mean1, rstd1, H1, Y2, mean2, rstd2, A)
+        return A
+
+    def inference(self, x):
+        """parametrized_adj.py:73-77: same forward without autograd (BN still in train mode)."""
+        return self.forward(x, keep=False)
+
+    # ---------------------------------------------------------------------------------- backward
+    def backward(self, dA):
+        """Returns (grads in parameters() order, dX)."""
+        K, n, d, h = self.K, self.n, self.d, self.h
+        x, Pa, Pb, mean1, rstd1, H1, Y2, mean2, rstd2, A = self._saved
+        W1, W2, w3 = self.W[0], self.W[1], self.W[2].view(-1)
+        dE = K.pge_symm_sigmoid_bwd(dA, A)
+        s1, s2, dw3, db3 = K.pge_l3_bwd_stats(Y2, dE, self.chunk_off, mean2, rstd2, self.gamma[1], self.beta[1], w3)
+        dgamma2, dbeta2 = s2.sum(0), s1.sum(0)
+        dY2 = K.pge_bn2_bwd_apply(Y2, dE, self.chunk_off, mean2, rstd2, self.gamma[1], self.beta[1], w3, s1, s2)
+        dW2 = K.gemm(dY2, H1, ta=True)                            # (h_out, h_in), K = N'^2
+        dH1 = K.gemm(dY2, W2)                                     # N'^2 x h
+        t1, t2 = K.pge_bn1_bwd_stats(dH1, Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0])
+        dgamma1, dbeta1 = t2.sum(0), t1.sum(0)
+        dPa, dPb = K.pge_bn1_bwd_reduce(dH1, Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0],
+                                        t1, t2)
+        dW1 = K.empty(h, 2 * d)
+        K.gemm(dPa, x, ta=True, out=dW1[:, :d])
+        K.gemm(dPb, x, ta=True, out=dW1[:, d:])
+        dX = K.gemm(dPa, W1[:, :d])
+        K.gemm(dPb, W1[:, d:], out=dX, beta=1.0)
+        zeros_h = K.zeros(h)                                      # biases ahead of a BatchNorm get exactly zero gradient
+        grads = [dW1, zeros_h, dW2, zeros_h.clone(), dw3.view(1, h), db3, dgamma1, dbeta1, dgamma2, dbeta2]
+        self._saved = None
+        return grads, dX

@@ -1,0 +1,202 @@
+"""Class-batch neighbour sampling for one outer step (host C++ in csrc/host_sampler.cpp).
+
+Replaces ``TransAndInd.retrieve_class_sampler`` (graphslim/dataset/loader.py:187-224) for all classes
+at once.  The class batch is ``np.random.permutation(members)[:256]`` (numpy's global legacy generator,
+as in the reference); neighbour draws come from torch's default CPU generator whose mt19937 state is
+checked out, advanced by the C++ sampler and written back, so both streams interleave exactly like the
+reference's.  Output arrays are packed into one pinned buffer and moved to HBM with a single copy.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import Csr
+
+_OFF_LEFT, _OFF_NEXT, _OFF_STATE = 8, 16, 24      # torch CPUGeneratorImpl serialised layout
+
+
+def fanouts(dataset, nlayers):
+    """loader.py:197-210."""
+    if nlayers == 1:
+        return [15]
+    if nlayers == 2:
+        return [15, 8] if dataset in ("reddit", "flickr") else [10, 5]
+    if nlayers in (3, 4, 5):
+        return {3: [15, 10, 5], 4: [15, 10, 5, 5], 5: [15, 10, 5, 5, 5]}[nlayers]
+    raise ValueError(f"nlayers={nlayers} has no fan-out schedule in the reference")
+
+
+class _TorchMt:
+    def __enter__(self):
+        raw = torch.get_rng_state().numpy().copy()
+        self.raw = raw
+        self.left = raw[_OFF_LEFT:_OFF_LEFT + 4].view(np.int32).copy()
+        self.next = raw[_OFF_NEXT:_OFF_NEXT + 8].view(np.uint64).astype(np.int32)
+        self.state = raw[_OFF_STATE:_OFF_STATE + 624 * 8].view(np.uint64).astype(np.uint32)
+        return self
+
+    def __exit__(self, *exc):
+        raw = self.raw
+        raw[_OFF_LEFT:_OFF_LEFT + 4] = self.left.view(np.uint8)
+        raw[_OFF_NEXT:_OFF_NEXT + 8] = self.next.astype(np.uint64).view(np.uint8)
+        raw[_OFF_STATE:_OFF_STATE + 624 * 8] = self.state.astype(np.uint64).view(np.uint8)
+        torch.set_rng_state(torch.from_numpy(raw))
+        return False
+
+
+class Block:
+    """One hop of the batched sampled structure: rows = level h nodes, cols = level h+1 nodes."""
+
+    def __init__(self, csr, csr_t, gcol):
+        self.csr, self.csr_t, self._gcol = csr, csr_t, gcol
+
+    def with_global_cols(self):
+        if self._gcol is None:
+            raise ValueError("only the outermost hop carries global column ids")
+        return Csr(self.csr.rowptr, self._gcol, self.csr.val, self.csr.n_rows, -1)
+
+
+class RealBatch:
+    pass
+
+
+class ClassSampler:
+    def __init__(self, adj_rowptr, adj_col, adj_val, members, dataset, nlayers, device, batch=256):
+        """adj_*: CSR of the normalised graph on the host (int64 rowptr, int32 col, fp32 val);
+        members[c]: node ids of class c (global ids in 'trans', train-local in 'ind')."""
+        self.lib = _lib.load()
+        self.rowptr = np.ascontiguousarray(adj_rowptr, dtype=np.int64)
+        self.col = np.ascontiguousarray(adj_col, dtype=np.int32)
+        self.val = np.ascontiguousarray(adj_val, dtype=np.float32)
+        self.n = self.rowptr.size - 1
+        self.members = [np.ascontiguousarray(m) for m in members]
+        self.n_class = len(members)
+        self.fan = np.asarray(fanouts(dataset, nlayers), dtype=np.int32)
+        self.nh = len(self.fan)
+        self.batch = batch
+        self.device = torch.device(device)
+        self.handle = self.lib.gs_sampler_create(self.n, self.rowptr.ctypes.data, self.col.ctypes.data,
+                                                 self.val.ctypes.data, self.nh, self.fan.ctypes.data)
+        if not self.handle:
+            raise _lib.GraphSlimLibraryError("gs_sampler_create failed")
+        # worst-case packed size
+        rows = min(batch, max(len(m) for m in self.members)) * self.n_class
+        cap, lvl = 0, rows
+        cap += 4 * (self.nh + 1) * (self.n_class + 1) + 64
+        for k in self.fan:
+            nnz = lvl * int(k)
+            cap += 4 * (lvl + 1) + 7 * 4 * nnz + 4 * (lvl + nnz + 1) + 8 * 16
+            lvl = lvl + nnz
+        cap += 4 * lvl + 3 * 4 * rows + 16 * 8
+        self.cap = int(cap)
+        # ring of pinned staging buffers: a buffer is reused only after its H2D copy has completed
+        self.ring = [torch.empty(self.cap, dtype=torch.uint8, pin_memory=self.device.type == "cuda")
+                     for _ in range(3 if self.device.type == "cuda" else 1)]
+        self.ring_events = [None] * len(self.ring)
+        self.ring_pos = 0
+        self.pinned = self.ring[0]
+        self.desc = np.empty(64, dtype=np.int64)
+        self.labels = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.gs_sampler_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def set_labels(self, labels):
+        """int32 label per graph node; the sampler then emits the labels of the target rows."""
+        self.labels = np.ascontiguousarray(labels, dtype=np.int32)
+        assert self.labels.size == self.n
+        self.lib.gs_sampler_set_labels(self.handle, self.labels.ctypes.data)
+
+    def draw_batches(self):
+        """np.random.permutation(class members)[:256] per class, in class order (loader.py:222)."""
+        parts = [np.random.permutation(m)[:self.batch].astype(np.int64) for m in self.members]
+        off = np.zeros(self.n_class + 1, dtype=np.int64)
+        off[1:] = np.cumsum([p.size for p in parts])
+        return np.concatenate(parts), off
+
+    def sample_host(self, materialise=None):
+        """Runs the sampler; returns (bytes_used, desc copy).  The packed arrays are in self.pinned."""
+        batch, off = self.draw_batches()
+        self.ring_pos = (self.ring_pos + 1) % len(self.ring)
+        if self.ring_events[self.ring_pos] is not None:
+            self.ring_events[self.ring_pos].synchronize()
+        self.pinned = self.ring[self.ring_pos]
+        mat = None
+        if materialise is not None:
+            mat = np.ascontiguousarray(materialise, dtype=np.uint8)
+        with _TorchMt() as g:
+            used = self.lib.gs_sampler_sample_step(self.handle, self.n_class, batch.ctypes.data, off.ctypes.data,
+                                                   mat.ctypes.data if mat is not None else None,
+                                                   g.state.ctypes.data, g.left.ctypes.data, g.next.ctypes.data,
+                                                   self.pinned.data_ptr(), self.cap, self.desc.ctypes.data)
+        if used < 0:
+            raise _lib.GraphSlimLibraryError(f"gs_sampler_sample_step failed with code {used}")
+        return int(used), self.desc.copy()
+
+    # ---- views --------------------------------------------------------------------------------
+    @staticmethod
+    def _view(buf, off, count, dtype):
+        nbytes = count * 4
+        return buf[off:off + nbytes].view(dtype)
+
+    def unpack(self, buf, desc, materialise=None):
+        """Build a RealBatch of tensor views over `buf` (host or device copy of the packed bytes)."""
+        nh, nc = self.nh, self.n_class
+        rb = RealBatch()
+        counts = [int(desc[2 + l]) for l in range(nh + 1)]
+        segs = self._view(buf, int(desc[8]), (nh + 1) * (nc + 1), torch.int32).view(nh + 1, nc + 1)
+        rb.counts = counts
+        rb.nid = self._view(buf, int(desc[9]), counts[nh], torch.int32)
+        rb.tcls = self._view(buf, int(desc[10]), counts[0], torch.int32)
+        rb.inv_b = self._view(buf, int(desc[11]), counts[0], torch.float32)
+        rb.target_ids = self._view(buf, int(desc[12]), counts[0], torch.int32)
+        rb.labels = self._view(buf, int(desc[13]), counts[0], torch.int32) if desc[13] >= 0 else None
+        blocks = []
+        for h in range(nh):
+            d = desc[16 + 8 * h: 24 + 8 * h]
+            nnz = int(d[0])
+            rows, cols = counts[h], counts[h + 1]
+            csr = Csr(self._view(buf, int(d[1]), rows + 1, torch.int32), self._view(buf, int(d[2]), nnz, torch.int32),
+                      self._view(buf, int(d[3]), nnz, torch.float32), rows, cols)
+            csr_t = Csr(self._view(buf, int(d[4]), cols + 1, torch.int32),
+                        self._view(buf, int(d[5]), nnz, torch.int32),
+                        self._view(buf, int(d[6]), nnz, torch.float32), cols, rows)
+            gcol = self._view(buf, int(d[7]), nnz, torch.int32) if d[7] >= 0 else None
+            blocks.append(Block(csr, csr_t, gcol))
+        rb.blocks = blocks
+        rb.blocks_fwd = blocks[::-1]          # application order: outermost hop first (adjs[::-1] in PyG)
+        # groups = materialised classes; per-level row segments restricted to them
+        if materialise is None:
+            keep = np.arange(nc)
+        else:
+            keep = np.nonzero(np.asarray(materialise))[0]
+        rb.class_ids = torch.tensor(keep, dtype=torch.int32, device=buf.device)
+        if len(keep) == nc:
+            rb.seg = [segs[l] for l in range(nh + 1)]
+        else:
+            # segments of skipped classes are empty, so dropping them keeps the offsets contiguous
+            idx = torch.tensor(np.concatenate([keep, [nc]]), dtype=torch.int64, device=buf.device)
+            rb.seg = [segs[l][idx].contiguous() for l in range(nh + 1)]
+        return rb
+
+    def sample(self, materialise=None):
+        """Full step: host sampling, one H2D copy of the packed bytes, device views."""
+        used, desc = self.sample_host(materialise)
+        if self.device.type == "cuda":
+            dev = torch.empty(used, dtype=torch.uint8, device=self.device)
+            dev.copy_(self.pinned[:used], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self.ring_events[self.ring_pos] = ev
+        else:
+            dev = self.pinned[:used].clone()
+        rb = self.unpack(dev, desc, materialise)
+        rb.h2d_bytes = used
+        return rb

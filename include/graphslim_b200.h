@@ -1,0 +1,196 @@
+/*
+ * graphslim_b200 -- C ABI of the B200-native GCond hot path.
+ *
+ * The reference (Emory-Melody/GraphSlim, pure Python) has no FFI of its own; its hot path
+ * bottoms out in third-party wheels (torch_sparse, ATen).  This header declares the
+ * entry points a binding for that path would bind, each citing the reference call site it
+ * replaces (paths relative to /root/reference/graphslim).  INTEGRATION.md shows the ctypes
+ * stub that wires them under the reference's GCond/GCondX classes.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every device pointer is caller-owned HBM
+ *   - matrices are row-major fp32 with an explicit leading dimension (elements)
+ *   - CSR indices are int32, values fp32
+ *   - `stream` is a cudaStream_t passed as void*; all launches are asynchronous on it
+ *   - return value: 0 on success, a positive cudaError_t, or a negative GS_E* code
+ *   - no hidden allocation, no global state
+ */
+#ifndef GRAPHSLIM_B200_H
+#define GRAPHSLIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_OK 0
+#define GS_EINVAL (-22)
+#define GS_ENOSPC (-28)
+#define GS_ENOSYS (-38)
+
+/* library / device --------------------------------------------------------------------- */
+int gs_version(void);
+/* Number of kernels this library has launched since the last reset (bench.py's gpu_launches). */
+int64_t gs_launch_count(void);
+void gs_launch_count_reset(void);
+const char* gs_last_error(void);
+
+/* ---- sparse propagation ----------------------------------------------------------------
+ * Y[r,:] (+)= sum_e val[e] * X[col[e],:]   for e in rowptr[r]..rowptr[r+1]
+ * replaces torch_sparse.matmul / SparseTensor.__matmul__ at models/sgc.py:47,51 and
+ * models/layers.py:41 (and the full-graph propagation of models/base.py:168-173).
+ * With `col` holding global node ids it also fuses the `features[n_id]` gather of
+ * condensation/gcond_base.py:214.  The backward w.r.t. the dense operand is the same call on
+ * the transposed structure (A_hat is symmetric for the full graph; sampled blocks get their
+ * transpose from gs_sample_step).
+ * chunk_row/chunk_beg/chunk_end (may be NULL): optional split of long rows into work items of
+ * bounded nnz (power-law tails); rows that are split must be listed consecutively and Y rows
+ * are accumulated with atomics, so Y must be zeroed by the caller when n_chunks > 0.       */
+int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val,
+                    const float* X, int64_t ldx, int32_t F, float* Y, int64_t ldy, int accumulate,
+                    int32_t n_chunks, const int32_t* chunk_row, const int32_t* chunk_beg,
+                    const int32_t* chunk_end, void* stream);
+
+/* Transpose-free backward through a rectangular block: dX[col[e],:] += val[e] * dY[r,:] (atomics).
+ * autograd of torch_sparse.matmul inside torch.autograd.grad at condensation/gcond_base.py:223. */
+int gs_spmm_csr_scatter_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val,
+                            const float* dY, int64_t ldy, int32_t F, float* dX, int64_t ldx, void* stream);
+
+/* out[i,:] = X[idx[i],:]   (features[n_id], condensation/gcond_base.py:214) */
+int gs_gather_rows_f32(int32_t n, const int32_t* idx, const float* X, int64_t ldx, int32_t F, float* out,
+                       int64_t ldo, void* stream);
+
+/* Symmetric GCN normalisation of CSR values on the device, bit-exact with utils.py:451-458:
+ * val_out[e] = (float)((r[row(e)] * (double)a[e]) * r[col[e]]) with r supplied in float64. */
+int gs_csr_gcn_norm_f64(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* a,
+                        const double* r, float* val_out, void* stream);
+
+/* ---- dense contractions ----------------------------------------------------------------
+ * C = alpha * op(A) * op(B) + beta * C, row-major, op = transpose when t? != 0.
+ * replaces the ATen matmuls of models/sgc.py:39,49, models/layers.py:40-46,377,
+ * models/parametrized_adj.py:57-71 and their autograd.
+ * precision: 0 = fp32 FMA (SIMT), 1 = tcgen05 3xBF16 split (fp32-class accuracy),
+ *            2 = tcgen05 single BF16 (looser, stated in DESIGN.md).                        */
+int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
+                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* stream);
+
+/* Grouped K-segmented product for per-class weight gradients:
+ * C[:, out_block[g]*N : (out_block[g]+1)*N] = A[seg[g]:seg[g+1], :M]^T * B[seg[g]:seg[g+1], :N]
+ * (autograd.grad w.r.t. layer weights, one class per group; condensation/gcond_base.py:223,234) */
+int gs_gemm_grouped_tn_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t M, int32_t N,
+                           const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                           void* stream);
+
+/* ---- small fused kernels of the condense model ------------------------------------------- */
+/* Z[r,c] += bias[c]; optional ReLU (models/layers.py:48-51,378-381; models/sgc.py:41) */
+int gs_bias_act_f32(int32_t rows, int32_t cols, float* Z, int64_t ldz, const float* bias, int relu, void* stream);
+/* D[r, g, c] *= (H[r,c] > 0) for g < groups  (ReLU backward, broadcast over the class axis) */
+int gs_relu_mask_f32(int32_t rows, int32_t groups, int32_t cols, float* D, const float* H, int64_t ldh,
+                     void* stream);
+/* S = softmax(Z) rowwise; R = (S - onehot(label)) * row_scale; nll[r] = -log S[r,label]
+ * (F.log_softmax + F.nll_loss and their gradient, models/sgc.py:57, gcond_base.py:221,228-231) */
+int gs_softmax_residual_f32(int32_t rows, int32_t C, const float* Z, int64_t ldz, const int32_t* label,
+                            const float* row_scale, float* S, float* R, float* nll, void* stream);
+/* E[r, blk[r]*C + c] = R[r,c], zero elsewhere (E is rows x nblk*C) */
+int gs_expand_class_blocks_f32(int32_t rows, int32_t C, int32_t nblk, const float* R, const int32_t* blk, float* E,
+                               void* stream);
+/* Q[r,c] = Zf[r, blk[r]*C + c] */
+int gs_pick_class_blocks_f32(int32_t rows, int32_t C, int32_t nblk, const float* Zf, const int32_t* blk, float* Q,
+                             void* stream);
+/* dZ[r,:] = S[r,:] * (q - <S[r,:], q>),  q = Q[r,:] * row_scale[r]   (softmax Jacobian-vector product) */
+int gs_softmax_jvp_f32(int32_t rows, int32_t C, const float* S, const float* Q, const float* row_scale, float* dZ,
+                       void* stream);
+
+/* ---- gradient matching (condensation/utils.py:12-106) ------------------------------------
+ * Column statistics of two (rows x cols) gradient matrices: stats[0..3][col] =
+ * <gs,gr>, |gs|^2, |gr|^2, |gs-gr|^2.                                                       */
+int gs_match_col_stats_f32(int32_t rows, int32_t cols, const float* gs, const float* gr, int64_t ld, float* stats,
+                           int64_t stats_ld, void* stream);
+/* Turns the statistics of all parameters into the loss and the per-column coefficients
+ * (alpha, beta) with  dLoss/dgs[:,j] = alpha[j]*gr[:,j] + beta[j]*gs[:,j].
+ * metric: 0 'ours', 1 'mse', 2 'cos'.  par_off[p]..par_off[p+1] = columns of parameter p in the packed
+ * stats; par_width[p] = per-class width; par_is_bias[p]; coeff[c] = n_c / N'.  loss_out += loss. */
+int gs_match_finalize_f32(int metric, int32_t n_par, const int32_t* par_off, const int32_t* par_width,
+                          const int32_t* par_is_bias, int32_t n_class, const float* coeff, const float* stats,
+                          int64_t stats_ld, float* alpha, float* beta, float* class_loss /* n_class scratch */,
+                          float* loss_out, void* stream);
+/* G[:,j] = alpha[j]*gr[:,j] + beta[j]*gs[:,j] */
+int gs_match_apply_f32(int32_t rows, int32_t cols, const float* gs, const float* gr, int64_t ld, const float* alpha,
+                       const float* beta, float* G, void* stream);
+
+/* ---- dense GCN normalisation (utils.py:429-439) and its backward --------------------------- */
+int gs_dense_gcn_norm_fwd_f32(int32_t n, const float* A, float* Ahat, float* r, void* stream);
+int gs_dense_gcn_norm_bwd_f32(int32_t n, const float* dAhat, const float* Ahat, const float* r, float* dA,
+                              float* work /* 2n floats */, void* stream);
+
+/* ---- PGE pairwise adjacency MLP (models/parametrized_adj.py:40-77) --------------------------
+ * Pair k = i*n + j has input [x_j, x_i]; layer 1 is evaluated in split form Pa[j] + Pb[i].
+ * Rows are processed in `nchunk` contiguous chunks with their own BatchNorm statistics
+ * (np.array_split semantics, parametrized_adj.py:41-55); chunk_off has nchunk+1 entries.     */
+/* BN1 batch statistics of Pa[j]+Pb[i] per chunk: mean/rstd (nchunk x h) */
+int gs_pge_l1_stats_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, int32_t nchunk,
+                        const int64_t* chunk_off, float eps, float* mean, float* rstd,
+                        double* work /* 2*nchunk*h */, void* stream);
+/* H1[k,:] = relu(gamma*(Pa[j]+Pb[i]-mean)*rstd + beta) */
+int gs_pge_l1_expand_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, int32_t nchunk,
+                         const int64_t* chunk_off, const float* mean, const float* rstd, const float* gamma,
+                         const float* beta, float* H1, void* stream);
+/* per-chunk column mean / rstd of Y (rows x h), biased variance */
+int gs_col_stats_chunked_f32(int64_t rows, int32_t h, const float* Y, int32_t nchunk, const int64_t* chunk_off,
+                             float eps, float* mean, float* rstd, double* work /* 2*nchunk*h */, void* stream);
+/* E[k] = relu(bn2(Y2[k,:])) . w3 + b3 */
+int gs_pge_l3_f32(int64_t rows, int32_t h, const float* Y2, int32_t nchunk, const int64_t* chunk_off,
+                  const float* mean, const float* rstd, const float* gamma, const float* beta, const float* w3,
+                  const float* b3, float* E, void* stream);
+/* A = sigmoid((E + E^T)/2) with zero diagonal */
+int gs_pge_symm_sigmoid_f32(int32_t n, const float* E, float* A, void* stream);
+/* dE = (T + T^T)/2, T = dA * A*(1-A) off-diagonal */
+int gs_pge_symm_sigmoid_bwd_f32(int32_t n, const float* dA, const float* A, float* dE, void* stream);
+/* layer-3 + BN2 backward statistics: per chunk s1 = sum dYhat, s2 = sum dYhat*xhat (overwritten);
+ * dw3 (h) and db3 (1) are accumulated into.  work: 2*nchunk*h + h + 1 doubles. */
+int gs_pge_l3_bwd_stats_f32(int64_t rows, int32_t h, const float* Y2, const float* dE, int32_t nchunk,
+                            const int64_t* chunk_off, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, const float* w3, float* s1, float* s2, float* dw3, float* db3,
+                            double* work, void* stream);
+/* dY2[k,:] = gamma*rstd*(dYhat - s1/m - xhat*s2/m) */
+int gs_pge_bn2_bwd_apply_f32(int64_t rows, int32_t h, const float* Y2, const float* dE, int32_t nchunk,
+                             const int64_t* chunk_off, const float* mean, const float* rstd, const float* gamma,
+                             const float* beta, const float* w3, const float* s1, const float* s2, float* dY2,
+                             void* stream);
+/* BN1 backward statistics from dH1 (rows x h): s1 = sum dYhat1, s2 = sum dYhat1*xhat1 per chunk */
+int gs_pge_bn1_bwd_stats_f32(int32_t n, int32_t h, const float* dH1, const float* Pa, const float* Pb, int32_t nchunk,
+                             const int64_t* chunk_off, const float* mean, const float* rstd, const float* gamma,
+                             const float* beta, float* s1, float* s2, double* work /* 2*nchunk*h */, void* stream);
+/* dPa[j,:] = sum_i dY1[i,j,:],  dPb[i,:] = sum_j dY1[i,j,:] */
+int gs_pge_bn1_bwd_reduce_f32(int32_t n, int32_t h, const float* dH1, const float* Pa, const float* Pb, int32_t nchunk,
+                              const int64_t* chunk_off, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, const float* s1, const float* s2, float* dPa, float* dPb,
+                              void* stream);
+
+/* ---- optimiser (torch.optim.Adam defaults; condensation/gcond_base.py:68-69, gcond.py:44) ---- */
+int gs_adam_step_f32(int64_t n, float* p, const float* g, float* m, float* v, int32_t step, double lr, double beta1,
+                     double beta2, double eps, void* stream);
+/* y = a*x + b*y */
+int gs_axpby_f32(int64_t n, float a, const float* x, float b, float* y, void* stream);
+
+/* ---- host side: bit-exact class / neighbour selection (dataset/loader.py:187-224) ------------
+ * One call samples the blocks of every class of one outer step, drawing from an mt19937 state in the
+ * layout of torch's CPU generator so the random stream interleaves exactly like the reference's.  */
+typedef struct gs_sampler gs_sampler;
+gs_sampler* gs_sampler_create(int32_t n_nodes, const int64_t* rowptr, const int32_t* col, const float* val,
+                              int32_t n_hops, const int32_t* fanout);
+void gs_sampler_destroy(gs_sampler* s);
+/* optional: int32 label per node; the labels of the target rows are then emitted with every step */
+void gs_sampler_set_labels(gs_sampler* s, const int32_t* labels);
+/* batch: concatenated class batches (node ids), batch_off[n_class+1]; materialise[c] != 0 selects the classes
+ * whose blocks are written (others only advance the generator).  out: packed buffer of `out_cap` bytes;
+ * desc: int64[64] table describing where each array landed.  Returns bytes used or a negative code. */
+int64_t gs_sampler_sample_step(gs_sampler* s, int32_t n_class, const int64_t* batch, const int64_t* batch_off,
+                               const uint8_t* materialise, uint32_t* mt_state, int32_t* mt_left, int32_t* mt_next,
+                               uint8_t* out, int64_t out_cap, int64_t* desc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,296 @@
+"""TEST INFRASTRUCTURE: plain-PyTorch fp32 reference of every kernel in graphslim_b200.ops.CudaOps.
+
+Two uses:
+  * ``-m gpu`` tests compare each CUDA kernel against the method of the same name here;
+  * ``-m "not gpu"`` tests run the host-side engine (closed-form matching, PGE backward, loops) on top of these
+    references to check the *algebra* against the oracle where no GPU exists.
+It is never imported by the product package; the product has no CPU path.
+"""
+import numpy as np
+import torch
+
+from graphslim_b200.ops import Csr
+
+
+class EmuOps:
+    def __init__(self, device="cpu", precision=0):
+        self.device = torch.device(device)
+        self.precision = precision
+        self._launches = 0
+
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=torch.float32):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def launches(self):
+        return self._launches
+
+    # ---- dense
+    def gemm(self, A, B, ta=False, tb=False, out=None, alpha=1.0, beta=0.0, precision=None):
+        a = A.T if ta else A
+        b = B.T if tb else B
+        r = alpha * (a @ b)
+        if out is None:
+            return r
+        if beta == 0.0:
+            out.copy_(r)
+        else:
+            out.mul_(beta).add_(r)
+        return out
+
+    def gemm_grouped_tn(self, A, B, seg, out_block, nblk):
+        M, N = A.shape[1], B.shape[1]
+        out = torch.zeros(M, nblk * N, device=self.device)
+        seg = seg.tolist()
+        for g, ob in enumerate(out_block.tolist()):
+            r0, r1 = seg[g], seg[g + 1]
+            out[:, ob * N:(ob + 1) * N] = A[r0:r1].T @ B[r0:r1]
+        return out
+
+    # ---- sparse
+    @staticmethod
+    def _coo(csr):
+        counts = (csr.rowptr[1:] - csr.rowptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(csr.n_rows, device=csr.rowptr.device), counts)
+        return rows, csr.col.long()
+
+    def spmm(self, csr, X, out=None, accumulate=False):
+        rows, cols = self._coo(csr)
+        y = torch.zeros(csr.n_rows, X.shape[1], device=self.device)
+        y.index_add_(0, rows, csr.val[:, None] * X[cols])
+        if out is None:
+            return y
+        if accumulate:
+            out.add_(y)
+        else:
+            out.copy_(y)
+        return out
+
+    def spmm_scatter(self, csr, dY, out):
+        rows, cols = self._coo(csr)
+        out.index_add_(0, cols, csr.val[:, None] * dY[rows])
+        return out
+
+    def gather_rows(self, X, idx):
+        return X[idx.long()].contiguous()
+
+    def csr_gcn_norm(self, rowptr, col, a, r64):
+        counts = (rowptr[1:] - rowptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(rowptr.numel() - 1, device=rowptr.device), counts)
+        return ((r64[rows] * a.double()) * r64[col.long()]).float()
+
+    # ---- glue
+    def bias_act(self, Z, bias, relu):
+        if bias is not None:
+            Z.add_(bias)
+        if relu:
+            Z.clamp_(min=0)
+        return Z
+
+    def relu_mask(self, D, H, groups=1):
+        rows, cols = H.shape
+        v = D.view(rows, groups, cols)
+        v.mul_((H > 0).to(D.dtype)[:, None, :])
+        return D
+
+    def softmax_residual(self, Z, labels, row_scale, want_nll=False):
+        ls = torch.log_softmax(Z, dim=1)
+        S = ls.exp()
+        Y = torch.zeros_like(S)
+        Y[torch.arange(Z.shape[0]), labels.long()] = 1.0
+        sc = row_scale[:, None] if row_scale is not None else 1.0
+        R = (S - Y) * sc
+        if want_nll:
+            return S, R, -ls[torch.arange(Z.shape[0]), labels.long()]
+        return S, R
+
+    def expand_class_blocks(self, R, blk, nblk):
+        rows, C = R.shape
+        E = torch.zeros(rows, nblk, C, device=self.device)
+        E[torch.arange(rows), blk.long()] = R
+        return E.view(rows, nblk * C)
+
+    def pick_class_blocks(self, Zf, blk, nblk):
+        rows = Zf.shape[0]
+        C = Zf.shape[1] // nblk
+        return Zf.view(rows, nblk, C)[torch.arange(rows), blk.long()].contiguous()
+
+    def softmax_jvp(self, S, Q, row_scale):
+        q = Q * (row_scale[:, None] if row_scale is not None else 1.0)
+        return S * (q - (S * q).sum(1, keepdim=True))
+
+    # ---- matching
+    def match(self, gs_list, gr_list, widths, is_bias, coeff, metric, loss_accum):
+        nc = coeff.numel()
+        out = []
+        eps = 1e-6
+        if metric == "cos":
+            dot = torch.zeros(nc)
+            ns2 = torch.zeros(nc)
+            nr2 = torch.zeros(nc)
+            for a, b, w in zip(gs_list, gr_list, widths):
+                av, bv = a.reshape(a.shape[0], nc, w), b.reshape(b.shape[0], nc, w)
+                dot += (av * bv).sum((0, 2))
+                ns2 += (av * av).sum((0, 2))
+                nr2 += (bv * bv).sum((0, 2))
+            ns, nr = ns2.sqrt(), nr2.sqrt()
+            den = ns * nr + eps
+            loss_accum += (coeff * (1 - dot / den)).sum()
+            al = -coeff / den
+            be = torch.where(ns > 0, coeff * dot * nr / (ns * den * den), torch.zeros_like(ns))
+            for a, b, w in zip(gs_list, gr_list, widths):
+                A_ = al.repeat_interleave(w)[None, :]
+                B_ = be.repeat_interleave(w)[None, :]
+                out.append(A_ * b + B_ * a)
+            return out
+        for a, b, w, bias in zip(gs_list, gr_list, widths, is_bias):
+            co = coeff.repeat_interleave(w)
+            if metric == "mse":
+                loss_accum += (co[None, :] * (a - b) ** 2).sum()
+                out.append(2 * co[None, :] * (a - b))
+                continue
+            if bias:
+                out.append(torch.zeros_like(a))
+                continue
+            dot = (a * b).sum(0)
+            ns, nr = a.norm(dim=0), b.norm(dim=0)
+            den = ns * nr + eps
+            loss_accum += (co * (1 - dot / den)).sum()
+            al = -co / den
+            be = torch.where(ns > 0, co * dot * nr / (ns * den * den), torch.zeros_like(ns))
+            out.append(al[None, :] * b + be[None, :] * a)
+        return out
+
+    # ---- dense norm
+    def dense_gcn_norm(self, A):
+        n = A.shape[0]
+        mx = A + torch.eye(n, device=self.device)
+        r = mx.sum(1).pow(-0.5)
+        r[torch.isinf(r)] = 0.0
+        return (r[:, None] * mx) * r[None, :], r
+
+    def dense_gcn_norm_bwd(self, dAhat, Ahat, r):
+        rd = (dAhat * Ahat).sum(1)
+        cd = (dAhat * Ahat).sum(0)
+        drho = -0.5 * r * r * (rd + cd)
+        return r[:, None] * r[None, :] * dAhat + drho[:, None]
+
+    # ---- PGE
+    @staticmethod
+    def _chunks(chunk_off):
+        o = chunk_off.tolist()
+        return list(zip(o[:-1], o[1:]))
+
+    @staticmethod
+    def _y1(Pa, Pb):
+        n, h = Pa.shape
+        return (Pb[:, None, :] + Pa[None, :, :]).reshape(n * n, h)       # row k = i*n + j -> Pa[j] + Pb[i]
+
+    def _stats(self, Y, chunk_off, eps):
+        mean, rstd = [], []
+        for a, b in self._chunks(chunk_off):
+            y = Y[a:b].double()
+            mean.append(y.mean(0))
+            rstd.append(1.0 / torch.sqrt(y.var(0, unbiased=False) + eps))
+        return torch.stack(mean).float(), torch.stack(rstd).float()
+
+    def _per_row(self, v, chunk_off, rows):
+        """(nchunk, h) -> (rows, h) by chunk membership."""
+        out = torch.empty(rows, v.shape[1], device=self.device)
+        for c, (a, b) in enumerate(self._chunks(chunk_off)):
+            out[a:b] = v[c]
+        return out
+
+    def pge_l1_stats(self, Pa, Pb, chunk_off, eps=1e-5):
+        return self._stats(self._y1(Pa, Pb), chunk_off, eps)
+
+    def pge_l1_expand(self, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
+        y = self._y1(Pa, Pb)
+        rows = y.shape[0]
+        xh = (y - self._per_row(mean, chunk_off, rows)) * self._per_row(rstd, chunk_off, rows)
+        return torch.relu(gamma * xh + beta)
+
+    def col_stats_chunked(self, Y, chunk_off, eps=1e-5):
+        return self._stats(Y, chunk_off, eps)
+
+    def pge_l3(self, Y2, chunk_off, mean, rstd, gamma, beta, w3, b3):
+        rows = Y2.shape[0]
+        xh = (Y2 - self._per_row(mean, chunk_off, rows)) * self._per_row(rstd, chunk_off, rows)
+        return torch.relu(gamma * xh + beta) @ w3 + b3
+
+    def pge_symm_sigmoid(self, E, n):
+        e = E.view(n, n)
+        a = torch.sigmoid((e + e.T) / 2)
+        return a - torch.diag(torch.diag(a))
+
+    def pge_symm_sigmoid_bwd(self, dA, A):
+        n = A.shape[0]
+        t = dA * A * (1 - A) * (1 - torch.eye(n, device=self.device))
+        return ((t + t.T) / 2).reshape(-1)
+
+    def _l3_common(self, Y2, dE, chunk_off, mean, rstd, gamma, beta, w3):
+        rows = Y2.shape[0]
+        xh = (Y2 - self._per_row(mean, chunk_off, rows)) * self._per_row(rstd, chunk_off, rows)
+        yh = gamma * xh + beta
+        dyh = dE[:, None] * w3[None, :] * (yh > 0)
+        return xh, yh, dyh
+
+    def pge_l3_bwd_stats(self, Y2, dE, chunk_off, mean, rstd, gamma, beta, w3):
+        xh, yh, dyh = self._l3_common(Y2, dE, chunk_off, mean, rstd, gamma, beta, w3)
+        s1 = torch.stack([dyh[a:b].sum(0) for a, b in self._chunks(chunk_off)])
+        s2 = torch.stack([(dyh[a:b] * xh[a:b]).sum(0) for a, b in self._chunks(chunk_off)])
+        dw3 = (dE[:, None] * torch.relu(yh)).sum(0)
+        db3 = dE.sum().view(1)
+        return s1, s2, dw3, db3
+
+    def pge_bn2_bwd_apply(self, Y2, dE, chunk_off, mean, rstd, gamma, beta, w3, s1, s2):
+        rows = Y2.shape[0]
+        xh, yh, dyh = self._l3_common(Y2, dE, chunk_off, mean, rstd, gamma, beta, w3)
+        m = torch.empty(rows, 1)
+        for a, b in self._chunks(chunk_off):
+            m[a:b] = float(b - a)
+        S1, S2 = self._per_row(s1, chunk_off, rows), self._per_row(s2, chunk_off, rows)
+        return gamma * self._per_row(rstd, chunk_off, rows) * (dyh - S1 / m - xh * S2 / m)
+
+    def _bn1_common(self, dH1, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
+        y = self._y1(Pa, Pb)
+        rows = y.shape[0]
+        xh = (y - self._per_row(mean, chunk_off, rows)) * self._per_row(rstd, chunk_off, rows)
+        dyh = dH1 * ((gamma * xh + beta) > 0)
+        return xh, dyh
+
+    def pge_bn1_bwd_stats(self, dH1, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
+        xh, dyh = self._bn1_common(dH1, Pa, Pb, chunk_off, mean, rstd, gamma, beta)
+        s1 = torch.stack([dyh[a:b].sum(0) for a, b in self._chunks(chunk_off)])
+        s2 = torch.stack([(dyh[a:b] * xh[a:b]).sum(0) for a, b in self._chunks(chunk_off)])
+        return s1, s2
+
+    def pge_bn1_bwd_reduce(self, dH1, Pa, Pb, chunk_off, mean, rstd, gamma, beta, s1, s2):
+        n, h = Pa.shape
+        rows = n * n
+        xh, dyh = self._bn1_common(dH1, Pa, Pb, chunk_off, mean, rstd, gamma, beta)
+        m = torch.empty(rows, 1)
+        for a, b in self._chunks(chunk_off):
+            m[a:b] = float(b - a)
+        S1, S2 = self._per_row(s1, chunk_off, rows), self._per_row(s2, chunk_off, rows)
+        dY1 = gamma * self._per_row(rstd, chunk_off, rows) * (dyh - S1 / m - xh * S2 / m)
+        dY1 = dY1.view(n, n, h)                                            # [i, j, :]
+        return dY1.sum(0), dY1.sum(1)                                     # dPa[j], dPb[i]
+
+    # ---- optimiser
+    def adam_step(self, p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        m.lerp_(g, 1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        bc1 = 1 - beta1 ** step
+        bc2 = 1 - beta2 ** step
+        denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
+        p.addcdiv_(m, denom, value=-(lr / bc1))
+
+    def axpby(self, a, x, b, y):
+        if b == 0.0:
+            y.copy_(a * x)
+        else:
+            y.mul_(b).add_(a * x)
+        return y

@@ -168,20 +168,18 @@ class GCondBase:
             self.trace("norm", rowptr=a_indptr, col=a_indices, val=val_host)
 
     # ------------------------------------------------------------------ one matching step (gcond_base.py:156-241)
-    def match_step(self, model, materialise=None):
-        """Returns (loss device scalar, dX, dA_hat) for the current feat_syn / adj_syn / model weights."""
+    def match_step(self, model):
+        """Returns (loss device scalar, dX, dA_hat, batch) for the current feat_syn / adj_syn / model weights.
+        With class sharding (model.lay.mask) only the owned classes are sampled in full and matched."""
         K = self.K
-        rb = self.sampler.sample(materialise)
+        rb = self.sampler.sample(model.lay.mask)
         if self.trace:
             self.trace("sample", rb=rb)
         gr = model.real_grads(rb, self.features, self.ones_full)
         model.syn_forward(self.feat_syn, self.adj_syn)
         gs = model.syn_grads()
         loss = K.zeros(1)
-        coeff = model.lay.coeff
-        if materialise is not None:
-            coeff = coeff * torch.as_tensor(np.asarray(materialise, dtype=np.float32), device=K.device)
-        G = K.match(gs, gr, model.widths, model.is_bias, coeff, self.args.dis_metric, loss)
+        G = K.match(gs, gr, model.widths, model.is_bias, model.lay.coeff, self.args.dis_metric, loss)
         dX, dA = model.syn_backward(G, need_dA=not model.identity_adj)
         return loss, dX, dA, rb
 

@@ -68,7 +68,8 @@ __global__ void pick_class_blocks_kernel(int rows, int C, int nblk, const float*
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * C) return;
   const int r = (int)(i / C), c = (int)(i % C);
-  Q[i] = Zf[(int64_t)r * nblk * C + (int64_t)blk[r] * C + c];
+  const int b = blk[r];
+  Q[i] = (b >= 0) ? Zf[(int64_t)r * nblk * C + (int64_t)b * C + c] : 0.f;
 }
 
 __global__ void softmax_jvp_kernel(int rows, int C, const float* __restrict__ S, const float* __restrict__ Q,

@@ -23,16 +23,24 @@ def _ones_col(K, n):
 class ClassLayout:
     """Row -> class bookkeeping of the synthetic nodes (labels_syn is a run of classes)."""
 
-    def __init__(self, K, labels_syn, n_class):
+    def __init__(self, K, labels_syn, n_class, owned=None):
+        """owned: class ids this rank matches (class sharding); None = every class.  Class-column matrices carry one
+        block per owned class; rows of other classes get block index -1 and contribute nothing."""
         dev = K.device
         lab = torch.as_tensor(labels_syn, dtype=torch.int64)
         self.n = lab.numel()
         self.n_class = int(n_class)
+        self.owned = list(range(self.n_class)) if owned is None else sorted(int(c) for c in owned)
+        self.nblk = len(self.owned)
+        local = torch.full((self.n_class,), -1, dtype=torch.int64)
+        local[torch.tensor(self.owned, dtype=torch.int64)] = torch.arange(self.nblk)
         counts = torch.bincount(lab, minlength=self.n_class).to(torch.float32)
         self.labels = lab.to(torch.int32).to(dev)
+        self.blk = local[lab].to(torch.int32).to(dev)           # row -> class-column block (or -1)
         self.inv_nc_row = (1.0 / counts[lab]).to(dev)          # 1/n_c per synthetic row (nll mean over the class)
-        self.coeff = (counts / float(self.n)).to(dev)           # n_c / N'   (gcond_base.py:237)
+        self.coeff = (counts / float(self.n))[torch.tensor(self.owned, dtype=torch.int64)].to(dev)   # n_c / N'
         self.inv_n_row = torch.full((self.n,), 1.0 / self.n, dtype=torch.float32, device=dev)
+        self.mask = None if owned is None else [1 if c in set(self.owned) else 0 for c in range(self.n_class)]
 
 
 class RealBatch:
@@ -84,8 +92,8 @@ class SGC1(_ModelBase):
         Z = K.gemm(T, W)
         K.gemm(t, b.view(1, -1), out=Z, beta=1.0)
         _, R = K.softmax_residual(Z, rb.labels, rb.inv_b)
-        gW = K.gemm_grouped_tn(T, R, rb.seg[0], rb.class_ids, self.C)
-        gb = K.gemm_grouped_tn(t, R, rb.seg[0], rb.class_ids, self.C)
+        gW = K.gemm_grouped_tn(T, R, rb.seg[0], rb.out_block, self.lay.nblk)
+        gb = K.gemm_grouped_tn(t, R, rb.seg[0], rb.out_block, self.lay.nblk)
         return [gW, gb]
 
     def syn_forward(self, X, A):
@@ -106,7 +114,7 @@ class SGC1(_ModelBase):
     def syn_grads(self):
         K, lay = self.K, self.lay
         self.S, self.R = K.softmax_residual(self.Z, lay.labels, lay.inv_nc_row)
-        self.Rexp = K.expand_class_blocks(self.R, lay.labels, self.C)
+        self.Rexp = K.expand_class_blocks(self.R, lay.blk, lay.nblk)
         gW = K.gemm(self.T[-1], self.Rexp, ta=True)
         gb = K.gemm(self.t[-1], self.Rexp, ta=True)
         return [gW, gb]
@@ -118,7 +126,7 @@ class SGC1(_ModelBase):
         H, u = self.T[-1], self.t[-1]
         Zt = K.gemm(H, GW)
         K.gemm(u, Gb, out=Zt, beta=1.0)
-        q = K.pick_class_blocks(Zt, lay.labels, self.C)
+        q = K.pick_class_blocks(Zt, lay.blk, lay.nblk)
         dZ = K.softmax_jvp(self.S, q, lay.inv_nc_row)
         dT = K.gemm(self.Rexp, GW, tb=True)
         K.gemm(dZ, W, tb=True, out=dT, beta=1.0)
@@ -161,13 +169,13 @@ class SGC2(_ModelBase):
         dU = R
         for blk in reversed(rb.blocks_fwd):
             dU = K.spmm(blk.csr_t, dU)
-        seg, ids = rb.seg[-1], rb.class_ids
+        seg, ids, nb = rb.seg[-1], rb.out_block, self.lay.nblk
         ones = _ones_col(K, Xg.shape[0])
-        gW2 = K.gemm_grouped_tn(H1, dU, seg, ids, self.C)
-        gb2 = K.gemm_grouped_tn(ones, dU, seg, ids, self.C)
+        gW2 = K.gemm_grouped_tn(H1, dU, seg, ids, nb)
+        gb2 = K.gemm_grouped_tn(ones, dU, seg, ids, nb)
         dA1 = K.relu_mask(K.gemm(dU, W2, tb=True), H1)
-        gW1 = K.gemm_grouped_tn(Xg, dA1, seg, ids, self.C)
-        gb1 = K.gemm_grouped_tn(ones, dA1, seg, ids, self.C)
+        gW1 = K.gemm_grouped_tn(Xg, dA1, seg, ids, nb)
+        gb1 = K.gemm_grouped_tn(ones, dA1, seg, ids, nb)
         return [gW1, gb1, gW2, gb2]
 
     def syn_forward(self, X, A):
@@ -184,10 +192,10 @@ class SGC2(_ModelBase):
 
     def syn_grads(self):
         K, lay = self.K, self.lay
-        N, C, h, nc = self.X.shape[0], self.C, self.h, self.C
+        N, C, h, nc = self.X.shape[0], self.C, self.h, lay.nblk
         self.S, self.R = K.softmax_residual(self.Z, lay.labels, lay.inv_nc_row)
         self.dTz = [None] * (self.k + 1)
-        self.dTz[self.k] = K.expand_class_blocks(self.R, lay.labels, nc)
+        self.dTz[self.k] = K.expand_class_blocks(self.R, lay.blk, nc)
         for l in range(self.k, 0, -1):
             self.dTz[l - 1] = self._prop(self.A, self.dTz[l], transpose=True)
         dUc = self.dTz[0]                                         # (N, nc*C)
@@ -203,7 +211,7 @@ class SGC2(_ModelBase):
         K, lay = self.K, self.lay
         W1, b1, W2, b2 = self.W
         G1, g1, G2, g2 = G
-        N, C, h, nc = self.X.shape[0], self.C, self.h, self.C
+        N, C, h, nc = self.X.shape[0], self.C, self.h, lay.nblk
         ones = _ones_col(K, N)
         # tangent forward along G
         At = K.gemm(self.X, G1)
@@ -215,7 +223,7 @@ class SGC2(_ModelBase):
         Tt = [Ut]
         for _ in range(self.k):
             Tt.append(self._prop(self.A, Tt[-1]))
-        q = K.pick_class_blocks(Tt[-1], lay.labels, nc)
+        q = K.pick_class_blocks(Tt[-1], lay.blk, nc)
         dZ = K.softmax_jvp(self.S, q, lay.inv_nc_row)
         # reverse through the tangent network (its cotangents are the first-order quantities)
         dA = None
@@ -268,15 +276,15 @@ class GCN2(_ModelBase):
         M2 = K.gemm(H1, W2)
         Z = K.bias_act(K.spmm(inner.csr, M2), b2, relu=False)
         _, R = K.softmax_residual(Z, rb.labels, rb.inv_b)
-        ids = rb.class_ids
-        gb2 = K.gemm_grouped_tn(_ones_col(K, R.shape[0]), R, rb.seg[0], ids, self.C)
+        ids, nb = rb.out_block, self.lay.nblk
+        gb2 = K.gemm_grouped_tn(_ones_col(K, R.shape[0]), R, rb.seg[0], ids, nb)
         dM2 = K.spmm(inner.csr_t, R)
         seg1 = rb.seg[1]
         ones = _ones_col(K, T2.shape[0])
-        gW2 = K.gemm_grouped_tn(H1, dM2, seg1, ids, self.C)
+        gW2 = K.gemm_grouped_tn(H1, dM2, seg1, ids, nb)
         dA1 = K.relu_mask(K.gemm(dM2, W2, tb=True), H1)
-        gb1 = K.gemm_grouped_tn(ones, dA1, seg1, ids, self.C)
-        gW1 = K.gemm_grouped_tn(T2, dA1, seg1, ids, self.C)
+        gb1 = K.gemm_grouped_tn(ones, dA1, seg1, ids, nb)
+        gW1 = K.gemm_grouped_tn(T2, dA1, seg1, ids, nb)
         return [gW1, gb1, gW2, gb2]
 
     def syn_forward(self, X, A):
@@ -291,9 +299,9 @@ class GCN2(_ModelBase):
 
     def syn_grads(self):
         K, lay = self.K, self.lay
-        N, C, h, nc = self.X.shape[0], self.C, self.h, self.C
+        N, C, h, nc = self.X.shape[0], self.C, self.h, lay.nblk
         self.S, self.R = K.softmax_residual(self.Z, lay.labels, lay.inv_nc_row)
-        self.Rexp = K.expand_class_blocks(self.R, lay.labels, nc)
+        self.Rexp = K.expand_class_blocks(self.R, lay.blk, nc)
         ones = _ones_col(K, N)
         gb2 = K.gemm(ones, self.Rexp, ta=True)
         self.dM2c = self._prop(self.A, self.Rexp, transpose=True)
@@ -309,7 +317,7 @@ class GCN2(_ModelBase):
         K, lay = self.K, self.lay
         W1, b1, W2, b2 = self.W
         G1, g1, G2, g2 = G
-        N, C, h, nc = self.X.shape[0], self.C, self.h, self.C
+        N, C, h, nc = self.X.shape[0], self.C, self.h, lay.nblk
         ones = _ones_col(K, N)
         M1t = K.gemm(self.X, G1)
         A1t = self._prop(self.A, M1t, fresh=True)
@@ -319,7 +327,7 @@ class GCN2(_ModelBase):
         K.gemm(self.H1, G2, out=M2t, beta=1.0)
         Zt = self._prop(self.A, M2t, fresh=True)
         K.gemm(ones, g2, out=Zt, beta=1.0)
-        q = K.pick_class_blocks(Zt, lay.labels, nc)
+        q = K.pick_class_blocks(Zt, lay.blk, nc)
         dZ = K.softmax_jvp(self.S, q, lay.inv_nc_row)
         dA = None
         if need_dA:

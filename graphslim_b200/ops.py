@@ -44,6 +44,26 @@ def _mat(t, name):
 METRIC_ID = {"ours": 0, "mse": 1, "cos": 2}
 
 
+class _Timed:
+    """``with K.timed(tag):`` brackets the enclosed launches with CUDA events when timing is switched on."""
+
+    def __init__(self, K, tag):
+        self.K, self.tag = K, tag
+
+    def __enter__(self):
+        self.on = getattr(self.K, "_timers", None) is not None
+        if self.on:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.K.device))
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record(torch.cuda.current_stream(self.K.device))
+            self.K._timers.setdefault(self.tag, []).append((self.a, self.b))
+        return False
+
+
 class CudaOps:
     """All device work of the GCond path.  ``precision``: 0 exact fp32 SIMT, 1 tcgen05 3xBF16, 2 tcgen05 BF16."""
 
@@ -68,6 +88,19 @@ class CudaOps:
 
     def launches(self):
         return int(self.lib.gs_launch_count())
+
+    # -- per-kernel device timing (bench.py roofline): CUDA events on the launching stream ---------
+    def start_timing(self):
+        self._timers = {}
+
+    def stop_timing(self):
+        """Synchronises and returns {tag: (launches, total_ms)}."""
+        timers, self._timers = getattr(self, "_timers", None) or {}, None
+        torch.cuda.synchronize(self.device)
+        return {tag: (len(ev), sum(a.elapsed_time(b) for a, b in ev)) for tag, ev in timers.items()}
+
+    def timed(self, tag):
+        return _Timed(self, tag)
 
     # -- dense ---------------------------------------------------------------------------------
     def gemm(self, A, B, ta=False, tb=False, out=None, alpha=1.0, beta=0.0, precision=None):

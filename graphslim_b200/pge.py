@@ -57,7 +57,8 @@ class PGE:
         Pb = K.gemm(x, W1[:, d:], tb=True)                       # second half: indexed by i (bias cancels in BN)
         mean1, rstd1 = K.pge_l1_stats(Pa, Pb, self.chunk_off, self.eps)
         H1 = K.pge_l1_expand(Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0])
-        Y2 = K.gemm(H1, self.W[1], tb=True)                      # the N'^2 x h x h product (bias cancels in BN)
+        with K.timed("pge_l2_fwd"):
+            Y2 = K.gemm(H1, self.W[1], tb=True)                  # the N'^2 x h x h product (bias cancels in BN)
         mean2, rstd2 = K.col_stats_chunked(Y2, self.chunk_off, self.eps)
         E = K.pge_l3(Y2, self.chunk_off, mean2, rstd2, self.gamma[1], self.beta[1], self.W[2].view(-1), self.b[2])
         A = K.pge_symm_sigmoid(E, n)
@@ -79,8 +80,10 @@ class PGE:
         s1, s2, dw3, db3 = K.pge_l3_bwd_stats(Y2, dE, self.chunk_off, mean2, rstd2, self.gamma[1], self.beta[1], w3)
         dgamma2, dbeta2 = s2.sum(0), s1.sum(0)
         dY2 = K.pge_bn2_bwd_apply(Y2, dE, self.chunk_off, mean2, rstd2, self.gamma[1], self.beta[1], w3, s1, s2)
-        dW2 = K.gemm(dY2, H1, ta=True)                            # (h_out, h_in), K = N'^2
-        dH1 = K.gemm(dY2, W2)                                     # N'^2 x h
+        with K.timed("pge_l2_bwd_dw"):
+            dW2 = K.gemm(dY2, H1, ta=True)                        # (h_out, h_in), K = N'^2
+        with K.timed("pge_l2_bwd_dx"):
+            dH1 = K.gemm(dY2, W2)                                 # N'^2 x h
         t1, t2 = K.pge_bn1_bwd_stats(dH1, Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0])
         dgamma1, dbeta1 = t2.sum(0), t1.sum(0)
         dPa, dPb = K.pge_bn1_bwd_reduce(dH1, Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0],

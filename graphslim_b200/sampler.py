@@ -99,6 +99,8 @@ class ClassSampler:
         self.pinned = self.ring[0]
         self.desc = np.empty(64, dtype=np.int64)
         self.labels = None
+        self.bytes_moved = 0              # host->device bytes of sampled blocks so far
+        self._group_cache = {}
 
     def __del__(self):
         try:
@@ -173,16 +175,20 @@ class ClassSampler:
         rb.blocks = blocks
         rb.blocks_fwd = blocks[::-1]          # application order: outermost hop first (adjs[::-1] in PyG)
         # groups = materialised classes; per-level row segments restricted to them
-        if materialise is None:
-            keep = np.arange(nc)
-        else:
-            keep = np.nonzero(np.asarray(materialise))[0]
-        rb.class_ids = torch.tensor(keep, dtype=torch.int32, device=buf.device)
-        if len(keep) == nc:
+        key = (None if materialise is None else tuple(int(m) for m in materialise), str(buf.device))
+        cached = self._group_cache.get(key)
+        if cached is None:          # constant across steps: build once (a fresh torch.tensor(...) would sync the stream)
+            keep = np.arange(nc) if materialise is None else np.nonzero(np.asarray(materialise))[0]
+            cached = (torch.tensor(keep, dtype=torch.int32, device=buf.device),
+                      torch.arange(len(keep), dtype=torch.int32, device=buf.device),
+                      torch.tensor(np.concatenate([keep, [nc]]), dtype=torch.int64, device=buf.device),
+                      len(keep) == nc)
+            self._group_cache[key] = cached
+        rb.class_ids, rb.out_block, idx, all_classes = cached      # out_block: class-column block per group
+        if all_classes:
             rb.seg = [segs[l] for l in range(nh + 1)]
         else:
             # segments of skipped classes are empty, so dropping them keeps the offsets contiguous
-            idx = torch.tensor(np.concatenate([keep, [nc]]), dtype=torch.int64, device=buf.device)
             rb.seg = [segs[l][idx].contiguous() for l in range(nh + 1)]
         return rb
 
@@ -199,4 +205,5 @@ class ClassSampler:
             dev = self.pinned[:used].clone()
         rb = self.unpack(dev, desc, materialise)
         rb.h2d_bytes = used
+        self.bytes_moved += used
         return rb

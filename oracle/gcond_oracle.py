@@ -354,7 +354,9 @@ class GCondOracle:
             loss = loss + (self.alloc[c] / self.n_syn) * match_loss(gw_syn, gw_real, args.dis_metric)
         return loss
 
-    def reduce(self, epochs=None):
+    def reduce(self, epochs=None, max_outer_steps=None):
+        """max_outer_steps: stop after that many outer steps (bounded CPU-baseline samples in bench.py)."""
+        import time
         args, data = self.args, self.data
         labels_syn = torch.from_numpy(self.labels_syn_np).long()
         if args.setting == "trans":
@@ -373,6 +375,8 @@ class GCondOracle:
         model = CondenseModel(args.condense_model, self.d, args.hidden, data.nclass, args.nlayers, args.ntrans)
         losses = []
         step = 0
+        self.step_done_at = []
+        self.loop_started_at = time.perf_counter()
         for it in range(args.epochs if epochs is None else epochs):
             model.initialize()
             self.obs("model_init", it, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).numpy())
@@ -401,6 +405,10 @@ class GCondOracle:
                     opt_model.zero_grad()
                     F.nll_loss(model(feat_inner, adj_inner), labels_syn).backward()
                     opt_model.step()
+                self.step_done_at.append(time.perf_counter())
+                if max_outer_steps is not None and step >= max_outer_steps:
+                    self.losses = losses
+                    return losses
         self.losses = losses
         return losses
 

@@ -27,6 +27,10 @@ class EmuOps:
     def launches(self):
         return self._launches
 
+    def timed(self, tag):
+        import contextlib
+        return contextlib.nullcontext()
+
     # ---- dense
     def gemm(self, A, B, ta=False, tb=False, out=None, alpha=1.0, beta=0.0, precision=None):
         a = A.T if ta else A
@@ -109,13 +113,16 @@ class EmuOps:
     def expand_class_blocks(self, R, blk, nblk):
         rows, C = R.shape
         E = torch.zeros(rows, nblk, C, device=self.device)
-        E[torch.arange(rows), blk.long()] = R
+        own = blk >= 0
+        E[torch.arange(rows)[own], blk.long()[own]] = R[own]
         return E.view(rows, nblk * C)
 
     def pick_class_blocks(self, Zf, blk, nblk):
         rows = Zf.shape[0]
         C = Zf.shape[1] // nblk
-        return Zf.view(rows, nblk, C)[torch.arange(rows), blk.long()].contiguous()
+        out = Zf.view(rows, nblk, C)[torch.arange(rows), blk.long().clamp(min=0)].contiguous()
+        out[blk < 0] = 0.0
+        return out
 
     def softmax_jvp(self, S, Q, row_scale):
         q = Q * (row_scale[:, None] if row_scale is not None else 1.0)

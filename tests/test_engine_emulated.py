@@ -53,10 +53,10 @@ def emulated(monkeypatch):
 FAST = [c for c in CASES if c != "cora_sgc1"]
 
 
-def run_case(name, epochs=None):
+def run_case(name, epochs=None, device="cpu", **extra):
     gold = helpers.golden(name)
     sub = int(gold["grad_subsample"])
-    args = helpers.case_args(name, save_init=False, progress=False)
+    args = helpers.case_args(name, device=device, save_init=False, progress=False, **extra)
     if epochs is not None:
         args.epochs = epochs
     raw = helpers.case_graph(name)
@@ -95,9 +95,7 @@ def run_case(name, epochs=None):
     return gold, sub, args, data, agent, seen, pge_init
 
 
-@pytest.mark.parametrize("name", FAST)
-def test_product_host_logic_matches_reference(name, emulated):
-    gold, sub, args, data, agent, seen, pge_init = run_case(name)
+def check_against_golden(gold, sub, args, data, agent, seen, pge_init, first_tol=1e-4, traj_tol=3e-2):
     # ---- integer / index work: bit exact
     assert np.array_equal(agent.labels_syn, gold["labels_syn"])
     assert list(agent.num_class_dict.keys()) == gold["class_order"].tolist()
@@ -118,17 +116,32 @@ def test_product_host_logic_matches_reference(name, emulated):
     assert np.array_equal(np.stack(seen["model_init"]), gold["model_init"])
     # ---- floating point
     losses = np.array(seen["losses"])
-    np.testing.assert_allclose(losses[:2], gold["losses"][:2], rtol=1e-4)
+    n = len(losses)
+    np.testing.assert_allclose(losses[:2], gold["losses"][:2], rtol=first_tol)
     # later steps compound fp32 reassociation through Adam (g/sqrt(v)); a looser bound applies to the trajectory
-    np.testing.assert_allclose(losses, gold["losses"], rtol=3e-2)
+    np.testing.assert_allclose(losses, gold["losses"][:n], rtol=traj_tol)
     for step, (fg, pg) in seen["grads"].items():
         ref = gold[f"g{step}_feat"]
-        tol = 1e-4 if step == 0 else 5e-3
+        tol = first_tol if step == 0 else max(5e-3, first_tol)
         np.testing.assert_allclose(fg, ref, rtol=tol, atol=tol * np.abs(ref).max())
         if pg.size:
             refp = gold[f"g{step}_pge"]
             gotp = pg[::sub]
             np.testing.assert_allclose(gotp, refp, rtol=tol, atol=tol * np.abs(refp).max())
-    # total RNG consumption identical to the reference run
-    assert np.array_equal(np.random.randint(0, 2**31 - 1, size=4).astype(np.int64), gold["np_rng_probe"])
-    assert np.array_equal(torch.randint(0, 2**31 - 1, (4,)).numpy(), gold["torch_rng_probe"])
+    if n == len(gold["losses"]):
+        # total RNG consumption identical to the reference run
+        assert np.array_equal(np.random.randint(0, 2**31 - 1, size=4).astype(np.int64), gold["np_rng_probe"])
+        assert np.array_equal(torch.randint(0, 2**31 - 1, (4,)).numpy(), gold["torch_rng_probe"])
+        # condensed features after the last epoch (feat_syn only moves once it % 50 >= 10, gcond.py:58-61)
+        # Trajectory-level agreement only: Adam's first steps move every entry by ~lr*sign(g), so entries whose
+        # gradient is at fp32-noise level legitimately differ by 2*lr after a few steps.
+        feat = agent.feat_syn.detach().cpu().numpy()[:, ::sub]
+        ref = gold["feat_final"]
+        rel = np.linalg.norm(feat - ref) / np.linalg.norm(ref)
+        print(f"feat_final relative Frobenius error {rel:.3e}")
+        assert rel < 0.15
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_product_host_logic_matches_reference(name, emulated):
+    check_against_golden(*run_case(name))

@@ -1,0 +1,64 @@
+"""World-size-2 class sharding on CPU (gloo): two ranks that each match half of the classes and all-reduce their
+partials reproduce the single-process run step for step (kernels replaced by their PyTorch references)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, name, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from graphslim_b200 import data as gdata
+    from graphslim_b200 import parallel
+    from graphslim_b200.condensation import gcond_base
+    from tests import helpers
+    from tests.emu_ops import EmuOps
+    gcond_base._kernels = lambda device, args: EmuOps(device)
+    args = helpers.case_args(name, save_init=False, progress=False)
+    args.epochs = 2
+    raw = helpers.case_graph(name)
+    data = gdata.TransAndInd(raw, args.dataset, args.pre_norm)
+    helpers.seed_everything(args.seed)
+    cls = parallel.ShardedGCondX if args.method == "gcondx" else parallel.ShardedGCond
+    agent = cls(args.setting, data, args)
+    losses = []
+    agent.trace = lambda kind, **kw: losses.append(float(kw["loss"].item())) if kind == "grads" else None
+    agent.reduce(data, verbose=False)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), losses=np.array(losses), feat=agent.feat_syn.numpy(),
+             owned=np.array(agent.owned_classes), pge=np.concatenate([p.numpy().ravel() for p in agent.pge.parameters()]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["mini_sgc2_arxiv", "mini_gcn_flickr"])
+def test_two_rank_class_sharding_matches_single_process(name, tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, name, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert set(r0["owned"]).isdisjoint(set(r1["owned"]))
+    # replicas stay identical
+    assert np.array_equal(r0["feat"], r1["feat"]) and np.array_equal(r0["pge"], r1["pge"])
+    np.testing.assert_array_equal(r0["losses"], r1["losses"])
+    # and match the single-process run on the same seed
+    from tests import helpers
+    gold = helpers.golden(name)
+    n = len(r0["losses"])
+    np.testing.assert_allclose(r0["losses"][:2], gold["losses"][:2], rtol=1e-4)
+    np.testing.assert_allclose(r0["losses"], gold["losses"][:n], rtol=3e-2)
+
+
+def test_partition_is_balanced_and_complete():
+    from graphslim_b200.parallel import partition_classes
+    sizes = [5000, 30, 256, 1000, 12, 255, 700, 90]
+    parts = partition_classes(sizes, 3)
+    assert sorted(c for p in parts for c in p) == list(range(8))
+    load = [sum(min(sizes[c], 256) for c in p) for p in parts]
+    assert max(load) - min(load) <= 256

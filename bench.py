@@ -159,10 +159,16 @@ def run_reference(ns):
 def spmm_probe(agent, pk, iters=10):
     """Standalone full-graph A_hat @ X on the workload's graph (BASELINE config 5 at this shape)."""
     import torch
+    from graphslim_b200.graph_utils import build_row_chunks
+    from graphslim_b200.ops import Csr
     K = agent.K
-    csr, X = agent.adj_csr, agent.features
+    X = agent.features
     n, F = X.shape
-    nnz = csr.col.numel()
+    base = agent.adj_csr
+    nnz = base.col.numel()
+    # power-law rows (max degree 1e4-1e5) are split into <=512-nnz work items
+    chunks = tuple(torch.from_numpy(a).to(K.device) for a in build_row_chunks(base.rowptr.cpu().numpy(), 512))
+    csr = Csr(base.rowptr, base.col, base.val, base.n_rows, base.n_cols, chunks)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=K.device)
     out = K.empty(n, F)
     ts = []
@@ -304,7 +310,9 @@ def run_ours(ns):
     line = {
         "metric": "gcond_condensation_epochs_per_sec", "value": value, "unit": "epochs/s", "n_gpus": world,
         "steps": K_, "warmup": W_, "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32" if ns.precision == 0 else ("bf16x3-split/f32-accum" if ns.precision == 1
+                                                                         else "bf16/f32-accum"),
+        "data": "synthetic",
         "config": {"workload": WORKLOADS[ns.workload], "parallelism": f"class-sharded x{world}" if world > 1 else
                    "single GPU", "gemm_precision": ns.precision,
                    "l2": "inputs exceed L2: per epoch the PGE streams N'^2 x h fp32 activations (>800 MB at the "
@@ -322,7 +330,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ogbn-arxiv", choices=list(WORKLOADS))
-    ap.add_argument("--precision", type=int, default=int(os.environ.get("GS_GEMM_PRECISION", "0")))
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("GS_GEMM_PRECISION", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ns = ap.parse_args()
     if ns.impl == "reference":

@@ -23,8 +23,9 @@ SIGNATURES = {
     "gs_spmm_csr_scatter_f32": (c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "gs_gather_rows_f32": (c_int, [c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "gs_csr_gcn_norm_f64": (c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gs_gemm_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_int]),
     "gs_gemm_f32": (c_int, [c_int, c_int, c_i32, c_i32, c_i32, c_f32, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_i64,
-                            c_int, c_vp]),
+                            c_int, c_vp, c_i64, c_vp]),
     "gs_gemm_grouped_tn_f32": (c_int, [c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "gs_bias_act_f32": (c_int, [c_i32, c_i32, c_vp, c_i64, c_vp, c_int, c_vp]),
     "gs_relu_mask_f32": (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),

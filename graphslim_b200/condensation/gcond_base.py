@@ -20,7 +20,7 @@ from ..sampler import ClassSampler
 
 def _kernels(device, args):
     """The only compute backend: CUDA kernels from libgraphslim_b200.so (raises on CPU / missing library)."""
-    return CudaOps(device, precision=int(getattr(args, "gemm_precision", 0)))
+    return CudaOps(device, precision=int(getattr(args, "gemm_precision", 1)))
 
 
 class _Adam:

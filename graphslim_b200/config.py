@@ -17,6 +17,8 @@ _DEFAULTS = dict(
     with_structure=1, lr=0.01, weight_decay=0.0, pre_norm=True, outer_loop=10, inner_loop=1,
     reduction_rate=-1.0, seed=1, nlayers=2, verbose=False, soft_label=0, init="random", eval_epochs=300,
     eval_model="GCN", run_inter_eval=5, eval_interval=100, alpha=0.1, attack=None, run_reduction=3,
+    # not a reference flag: arithmetic of the large dense products (0 fp32 SIMT, 1 tcgen05 3xBF16 split, 2 tcgen05 BF16)
+    gemm_precision=1,
 )
 
 _CITATION = dict(lr_feat=1e-4, lr_adj=1e-4, pre_norm=True, dis_metric="ours", outer_loop=20, inner_loop=15,

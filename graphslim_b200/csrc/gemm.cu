@@ -12,7 +12,9 @@
 namespace gs {
 
 int gemm_tc_dispatch(int ta, int tb, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B,
-                     int64_t ldb, float beta, float* C, int64_t ldc, int precision, cudaStream_t st);
+                     int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* workspace,
+                     int64_t workspace_bytes, cudaStream_t st);
+int64_t gemm_tc_workspace_bytes(int M, int N, int K, int precision);
 
 struct GemmProblem {
   int ta, tb;
@@ -156,7 +158,8 @@ static int launch_simt(GemmProblem& p, int gz, cudaStream_t st) {
 extern "C" {
 
 int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
-                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* stream) {
+                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* workspace,
+                int64_t workspace_bytes, void* stream) {
   GS_REQUIRE(M >= 0 && N >= 0 && K >= 0 && C && ldc >= N);
   GS_REQUIRE(K == 0 || (A && B));
   GS_REQUIRE(K == 0 || lda >= (ta ? M : K));
@@ -164,7 +167,8 @@ int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, co
   if (M == 0 || N == 0) return GS_OK;
   cudaStream_t st = gs::as_stream(stream);
   if (precision != 0) {
-    const int rc = gs::gemm_tc_dispatch(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, precision, st);
+    const int rc = gs::gemm_tc_dispatch(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, precision, workspace,
+                                        workspace_bytes, st);
     if (rc != GS_ENOSYS) return rc;  // GS_ENOSYS: shape not covered by the tensor-core kernels
   }
   gs::GemmProblem p{ta, tb, M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, 1, K, nullptr, nullptr};
@@ -191,6 +195,10 @@ int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, co
     }
   }
   return gs::launch_simt(p, p.splits, st);
+}
+
+int64_t gs_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K, int precision) {
+  return gs::gemm_tc_workspace_bytes(M, N, K, precision);
 }
 
 int gs_gemm_grouped_tn_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t M, int32_t N,

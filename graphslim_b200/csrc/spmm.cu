@@ -258,6 +258,7 @@ extern "C" {
 int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
                     int64_t ldx, int32_t F, float* Y, int64_t ldy, int accumulate, int32_t n_chunks,
                     const int32_t* chunk_row, const int32_t* chunk_beg, const int32_t* chunk_end, void* stream) {
+  if (n_rows == 0) return GS_OK;
   GS_REQUIRE(n_rows >= 0 && F > 0 && rowptr && X && Y && ldx >= F && ldy >= F);
   GS_REQUIRE(n_chunks == 0 || (chunk_row && chunk_beg && chunk_end));
   if (n_rows == 0) return GS_OK;
@@ -270,6 +271,7 @@ int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, c
 
 int gs_spmm_csr_scatter_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val,
                             const float* dY, int64_t ldy, int32_t F, float* dX, int64_t ldx, void* stream) {
+  if (n_rows == 0) return GS_OK;
   GS_REQUIRE(n_rows >= 0 && F > 0 && rowptr && dY && dX && ldx >= F && ldy >= F);
   if (n_rows == 0) return GS_OK;
   const int gx = (n_rows + gs::kWarpsPerBlock - 1) / gs::kWarpsPerBlock;
@@ -284,6 +286,7 @@ int gs_spmm_csr_scatter_f32(int32_t n_rows, const int32_t* rowptr, const int32_t
 
 int gs_gather_rows_f32(int32_t n, const int32_t* idx, const float* X, int64_t ldx, int32_t F, float* out, int64_t ldo,
                        void* stream) {
+  if (n == 0) return GS_OK;
   GS_REQUIRE(n >= 0 && F > 0 && idx && X && out && ldx >= F && ldo >= F);
   if (n == 0) return GS_OK;
   const int gx = (n + gs::kWarpsPerBlock - 1) / gs::kWarpsPerBlock;

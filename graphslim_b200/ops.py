@@ -117,9 +117,23 @@ class CudaOps:
         if out.shape != (M, N):
             raise ValueError(f"gemm output shape {tuple(out.shape)} != {(M, N)}")
         prec = self.precision if precision is None else precision
+        ws, ws_bytes = None, 0
+        if prec:
+            ws_bytes = int(self.lib.gs_gemm_workspace_bytes(M, N, K, prec))
+            if ws_bytes:
+                ws = self._gemm_workspace(ws_bytes)
         _lib.check(self.lib.gs_gemm_f32(int(ta), int(tb), M, N, K, alpha, _ptr(A), lda, _ptr(B), ldb, beta,
-                                        _ptr(out), ldc, prec, self.stream), "gs_gemm_f32")
+                                        _ptr(out), ldc, prec, _ptr(ws), ws_bytes, self.stream), "gs_gemm_f32")
         return out
+
+    def _gemm_workspace(self, nbytes):
+        """Scratch for the BF16 tile image of op(B); one buffer reused by every call on this stream (stream order
+        makes reuse safe: the next pack kernel runs after the previous GEMM has finished reading)."""
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, device=self.device)
+            self._ws = ws
+        return ws
 
     def gemm_grouped_tn(self, A, B, seg, out_block, nblk):
         """out[:, out_block[g]*N:(out_block[g]+1)*N] = A[seg[g]:seg[g+1]]^T @ B[seg[g]:seg[g+1]]; other blocks zero."""

@@ -71,9 +71,13 @@ int gs_csr_gcn_norm_f64(int32_t n_rows, const int32_t* rowptr, const int32_t* co
  * replaces the ATen matmuls of models/sgc.py:39,49, models/layers.py:40-46,377,
  * models/parametrized_adj.py:57-71 and their autograd.
  * precision: 0 = fp32 FMA (SIMT), 1 = tcgen05 3xBF16 split (fp32-class accuracy),
- *            2 = tcgen05 single BF16 (looser, stated in DESIGN.md).                        */
+ *            2 = tcgen05 single BF16 (looser, stated in DESIGN.md).
+ * workspace: device scratch of at least gs_gemm_workspace_bytes(M,N,K,precision) bytes (16-byte aligned) that
+ *            receives the BF16 tile image of op(B); may be NULL when that returns 0.           */
+int64_t gs_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K, int precision);
 int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
-                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* stream);
+                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* workspace,
+                int64_t workspace_bytes, void* stream);
 
 /* Grouped K-segmented product for per-class weight gradients:
  * C[:, out_block[g]*N : (out_block[g]+1)*N] = A[seg[g]:seg[g+1], :M]^T * B[seg[g]:seg[g+1], :N]

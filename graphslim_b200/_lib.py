@@ -58,6 +58,7 @@ SIGNATURES = {
     "gs_sampler_create": (c_vp, [c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "gs_sampler_destroy": (None, [c_vp]),
     "gs_sampler_set_labels": (None, [c_vp, c_vp]),
+    "gs_sampler_set_threads": (None, [c_vp, c_i32]),
     "gs_sampler_sample_step": (c_i64, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
 }
 

@@ -48,6 +48,22 @@ class GCond(GCondBase):
             self.trace("model_init", epoch=it, W=W)
         optimizer_model = _Adam(K, W, args.lr)                # fresh Adam every epoch (gcond.py:44)
         self._loss_dev.zero_()
+        # the epoch's class batches are sampled one outer step ahead on a worker thread (same random streams, same
+        # order); nothing else draws from numpy's / torch's generators until the epoch ends
+        self._prefetch = self.sampler.prefetch(outer_loop, model.lay.mask) if getattr(args, "prefetch", True) else None
+        try:
+            self._run_outer_steps(it, outer_loop, inner_loop, optimizer_model)
+        finally:
+            if self._prefetch is not None:
+                self._prefetch.join()
+                self._prefetch = None
+        if getattr(args, "track_loss", True):
+            # loss_avg is never reset in the reference (gcond.py:36,52,74); one host sync per epoch instead of
+            # the reference's loss.item() per outer step
+            self.loss_avg = (self.loss_avg + float(self._loss_dev.item())) / (self.data.nclass * outer_loop)
+
+    def _run_outer_steps(self, it, outer_loop, inner_loop, optimizer_model):
+        args, K, pge, model = self.args, self.K, self.pge, self.model
         for ol in range(outer_loop):
             if not self.x_variant:
                 adj_raw = pge.forward(self.feat_syn)
@@ -75,10 +91,6 @@ class GCond(GCondBase):
                 adj_inner, _ = K.dense_gcn_norm(self.adj_syn_inner)
             for _ in range(inner_loop):
                 optimizer_model.step(model.train_grads(self.feat_syn, adj_inner))
-        if getattr(args, "track_loss", True):
-            # loss_avg is never reset in the reference (gcond.py:36,52,74); one host sync per epoch instead of
-            # the reference's loss.item() per outer step
-            self.loss_avg = (self.loss_avg + float(self._loss_dev.item())) / (self.data.nclass * outer_loop)
 
     def publish(self, data):
         n = self.nnodes_syn

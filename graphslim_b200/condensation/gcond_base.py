@@ -172,7 +172,8 @@ class GCondBase:
         """Returns (loss device scalar, dX, dA_hat, batch) for the current feat_syn / adj_syn / model weights.
         With class sharding (model.lay.mask) only the owned classes are sampled in full and matched."""
         K = self.K
-        rb = self.sampler.sample(model.lay.mask)
+        pf = getattr(self, "_prefetch", None)
+        rb = pf.next() if pf is not None else self.sampler.sample(model.lay.mask)
         if self.trace:
             self.trace("sample", rb=rb)
         gr = model.real_grads(rb, self.features, self.ones_full)

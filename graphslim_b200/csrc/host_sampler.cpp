@@ -10,11 +10,23 @@
 //   * one mt19937 word `% j` per Floyd draw (torch::randint(0, j, {1})), drawn in row order;
 //   * the iteration order of libstdc++'s std::unordered_set<int64_t>, which fixes the order in
 //     which new nodes are discovered (and therefore which draws later rows receive).
-// Both are reproduced literally (same container type; generator state is imported/exported in
-// torch's serialised layout by the Python caller).
+// Both are reproduced literally (the real container, fed from a stack arena; generator state is
+// imported/exported in torch's serialised layout by the Python caller).
+//
+// Speed (this is the host-side bottleneck of an epoch once the GPU side is fast):
+//   * the generator stream is serial, but the number of draws a hop consumes depends only on the
+//     degrees of its rows.  All hops but the last are cheap (<= 256 * fanout rows per class) and run
+//     serially; for the last hop the stream is cut into per-class segments (state snapshot + discard),
+//     and the classes are then sampled in parallel by a small thread pool;
+//   * the sampler keeps its own interleaved (col,val) copy of the CSR and software-prefetches the
+//     rowptr / edge cache lines of a block of rows before consuming them: the work is otherwise
+//     dominated by ~2 DRAM misses per sampled edge.
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <memory_resource>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -23,7 +35,7 @@
 namespace {
 
 struct Mt19937 {
-  uint32_t* s;
+  uint32_t s[624];
   int32_t left, next;
   static inline uint32_t tw(uint32_t u, uint32_t v) {
     return (((u & 0x80000000u) | (v & 0x7fffffffu)) >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
@@ -44,6 +56,17 @@ struct Mt19937 {
     y ^= (y << 15) & 0xefc60000u;
     return y ^ (y >> 18);
   }
+  void discard(int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+      if (--left == 0) reload();
+      ++next;
+    }
+  }
+};
+
+struct ColVal {
+  int32_t col;
+  float val;
 };
 
 struct Entry {
@@ -51,32 +74,149 @@ struct Entry {
   int64_t e;
 };
 
+struct HopOut {
+  std::vector<int32_t> rowptr;   // local, starts at 0, n_rows + 1 entries
+  std::vector<int32_t> col;      // class-local column ids
+  std::vector<int32_t> gcol;     // global ids (last hop only)
+  std::vector<float> val;
+};
+
+struct ClassOut {
+  std::vector<int32_t> nid;                 // discovered nodes, level by level (prefix-stable)
+  std::vector<int32_t> level_count;         // nh + 1
+  std::vector<HopOut> hop;                  // nh
+};
+
+constexpr int kPrefetchBlock = 64;
+
 }  // namespace
 
 struct gs_sampler {
   int32_t n;
   const int64_t* rowptr;
-  const int32_t* col;
-  const float* val;
+  std::vector<ColVal> cv;                   // interleaved copy: one cache line per sampled edge instead of two
   int32_t nh;
   int32_t fan[8];
   const int32_t* labels = nullptr;
-  std::vector<int32_t> pos;  // node -> local index within the current class, -1 when unseen
+  std::vector<std::vector<int32_t>> pos;    // per worker: node -> class-local index, -1 when unseen
+  int n_workers = 1;
 };
+
+namespace {
+
+// One hop for one class.  `nid` = all nodes discovered so far (the rows), appended to in place.
+// out == nullptr: nothing is recorded (only nid / pos evolve and the generator advances).
+inline void sample_hop(const gs_sampler* S, std::vector<int32_t>& pos, Mt19937& rng, std::vector<int32_t>& nid, int32_t k,
+                       bool last, HopOut* out) {
+  const int64_t* rp = S->rowptr;
+  const ColVal* cv = S->cv.data();
+  const int32_t n_rows = (int32_t)nid.size();
+  std::vector<Entry> rowbuf;
+  rowbuf.reserve(32);
+  if (out) {
+    out->rowptr.clear();
+    out->rowptr.reserve((size_t)n_rows + 1);
+    out->rowptr.push_back(0);
+    out->col.clear();
+    out->val.clear();
+    out->gcol.clear();
+    out->col.reserve((size_t)n_rows * (size_t)k);
+    out->val.reserve((size_t)n_rows * (size_t)k);
+    if (last) out->gcol.reserve((size_t)n_rows * (size_t)k);
+  }
+  // block-wise: draw (needs only degrees) and prefetch the chosen edges, then consume them
+  int64_t chosen_e[kPrefetchBlock * 16];
+  int32_t chosen_n[kPrefetchBlock];
+  for (int32_t b0 = 0; b0 < n_rows; b0 += kPrefetchBlock) {
+    const int32_t b1 = std::min(n_rows, b0 + kPrefetchBlock);
+    for (int32_t t = b0; t < b1; ++t) __builtin_prefetch(rp + nid[(size_t)t]);
+    for (int32_t t = b0; t < b1; ++t) {
+      const int32_t v = nid[(size_t)t];
+      const int64_t beg = rp[v], deg = rp[v + 1] - beg;
+      alignas(16) unsigned char arena[2048];
+      std::pmr::monotonic_buffer_resource pool(arena, sizeof(arena));
+      std::pmr::unordered_set<int64_t> chosen(&pool);
+      if (deg <= k) {
+        for (int64_t j = 0; j < deg; ++j) chosen.insert(j);
+      } else {
+        for (int64_t j = deg - k; j < deg; ++j) {
+          const int64_t r = (int64_t)(rng() % (uint32_t)j);
+          if (!chosen.insert(r).second) chosen.insert(j);
+        }
+      }
+      int32_t cnt = 0;
+      int64_t* dst = chosen_e + (size_t)(t - b0) * 16;
+      for (const int64_t& p : chosen) {
+        const int64_t e = beg + p;
+        dst[cnt++] = e;
+        __builtin_prefetch(cv + e);
+      }
+      chosen_n[t - b0] = cnt;
+    }
+    for (int32_t t = b0; t < b1; ++t) {
+      const int64_t* src = chosen_e + (size_t)(t - b0) * 16;
+      const int32_t cnt = chosen_n[t - b0];
+      rowbuf.clear();
+      for (int32_t i = 0; i < cnt; ++i) {
+        const int64_t e = src[i];
+        const int32_t u = cv[e].col;
+        int32_t loc = pos[(size_t)u];
+        if (loc < 0) {
+          loc = (int32_t)nid.size();
+          pos[(size_t)u] = loc;
+          nid.push_back(u);
+        }
+        rowbuf.push_back(Entry{loc, e});
+      }
+      if (out) {
+        std::sort(rowbuf.begin(), rowbuf.end(), [](const Entry& a, const Entry& b) { return a.local < b.local; });
+        for (const Entry& en : rowbuf) {
+          out->col.push_back(en.local);
+          out->val.push_back(cv[en.e].val);
+          if (last) out->gcol.push_back(cv[en.e].col);
+        }
+        out->rowptr.push_back((int32_t)out->col.size());
+      }
+    }
+  }
+}
+
+inline int64_t count_draws(const gs_sampler* S, const std::vector<int32_t>& nid, int32_t k) {
+  const int64_t* rp = S->rowptr;
+  int64_t draws = 0;
+  const int32_t n_rows = (int32_t)nid.size();
+  for (int32_t b0 = 0; b0 < n_rows; b0 += 256) {
+    const int32_t b1 = std::min(n_rows, b0 + 256);
+    for (int32_t t = b0; t < b1; ++t) __builtin_prefetch(rp + nid[(size_t)t]);
+    for (int32_t t = b0; t < b1; ++t) {
+      const int64_t deg = rp[nid[(size_t)t] + 1] - rp[nid[(size_t)t]];
+      if (deg > k) draws += k;
+    }
+  }
+  return draws;
+}
+
+}  // namespace
 
 extern "C" {
 
 gs_sampler* gs_sampler_create(int32_t n_nodes, const int64_t* rowptr, const int32_t* col, const float* val,
                               int32_t n_hops, const int32_t* fanout) {
-  if (n_hops < 1 || n_hops > 5) return nullptr;
+  if (n_hops < 1 || n_hops > 5 || !rowptr || !col || !val) return nullptr;
+  for (int i = 0; i < n_hops; ++i)
+    if (fanout[i] < 0 || fanout[i] > 15) return nullptr;  // arena / block buffers are sized for the reference fan-outs
   gs_sampler* s = new gs_sampler();
   s->n = n_nodes;
   s->rowptr = rowptr;
-  s->col = col;
-  s->val = val;
+  const int64_t nnz = rowptr[n_nodes];
+  s->cv.resize((size_t)nnz);
+  for (int64_t e = 0; e < nnz; ++e) s->cv[(size_t)e] = ColVal{col[e], val[e]};
   s->nh = n_hops;
   for (int i = 0; i < n_hops; ++i) s->fan[i] = fanout[i];
-  s->pos.assign((size_t)n_nodes, -1);
+  unsigned hw = std::thread::hardware_concurrency();
+  s->n_workers = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
+  s->pos.assign((size_t)s->n_workers, std::vector<int32_t>());
+  s->pos[0].assign((size_t)n_nodes, -1);
   return s;
 }
 
@@ -86,168 +226,191 @@ void gs_sampler_set_labels(gs_sampler* s, const int32_t* labels) {
   if (s) s->labels = labels;
 }
 
+void gs_sampler_set_threads(gs_sampler* s, int32_t n) {
+  if (s && n >= 1) {
+    s->n_workers = n > 64 ? 64 : n;
+    if ((int)s->pos.size() < s->n_workers) s->pos.resize((size_t)s->n_workers);
+  }
+}
+
 static inline int64_t align16(int64_t x) { return (x + 15) & ~int64_t(15); }
 
 int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* batch, const int64_t* batch_off,
                                const uint8_t* materialise, uint32_t* mt_state, int32_t* mt_left, int32_t* mt_next,
                                uint8_t* out, int64_t out_cap, int64_t* desc) {
-  if (!S || !batch || !batch_off || !mt_state || !out || !desc) return GS_EINVAL;
-  Mt19937 rng{mt_state, *mt_left, *mt_next};
+  if (!S || !batch || !batch_off || !mt_state || !out || !desc || n_class < 1) return GS_EINVAL;
   const int nh = S->nh;
-  const int64_t* rp = S->rowptr;
-  const int32_t* gc = S->col;
-  const float* gv = S->val;
+  Mt19937 rng;
+  std::memcpy(rng.s, mt_state, sizeof(rng.s));
+  rng.left = *mt_left;
+  rng.next = *mt_next;
 
-  // batched outputs
-  std::vector<std::vector<int32_t>> seg(nh + 1, std::vector<int32_t>(n_class + 1, 0));
-  std::vector<int32_t> nid_all, tcls, target_ids;
-  std::vector<float> inv_b;
-  struct Blk {
-    std::vector<int32_t> rowptr{0}, col, gcol;
-    std::vector<float> val;
-  };
-  std::vector<Blk> blk(nh);
+  std::vector<ClassOut> co((size_t)n_class);
+  std::vector<Mt19937> snap((size_t)n_class);  // generator state at the start of each class's last hop
+  std::vector<uint8_t> keepv((size_t)n_class);
 
-  std::vector<int32_t> nid;  // node list of the current class (level by level, prefix-stable)
-  std::vector<Entry> rowbuf;
-  for (int32_t c = 0; c < n_class; ++c) {
-    const int64_t b0 = batch_off[c], b1 = batch_off[c + 1];
-    const bool keep = materialise == nullptr || materialise[c] != 0;
-    nid.clear();
-    for (int64_t t = b0; t < b1; ++t) {
-      const int32_t v = (int32_t)batch[t];
-      if (v < 0 || v >= S->n) return GS_EINVAL;
-      // duplicates cannot occur in a permutation slice; the reference's map would alias them
-      S->pos[v] = (int32_t)nid.size();
-      nid.push_back(v);
-    }
-    std::vector<int32_t> level_count(nh + 1, 0);
-    level_count[0] = (int32_t)nid.size();
-    for (int h = 0; h < nh; ++h) {
-      const int32_t k = S->fan[h];
-      const int32_t n_rows = (int32_t)nid.size();
-      const bool last = (h == nh - 1);
-      if (!keep && last) {
-        // only advance the generator: k draws for every row with more than k neighbours
-        int64_t draws = 0;
-        for (int32_t t = 0; t < n_rows; ++t) {
-          const int64_t deg = rp[nid[t] + 1] - rp[nid[t]];
-          if (deg > k) draws += k;
-        }
-        for (int64_t i = 0; i < draws; ++i) (void)rng();
-        break;
+  // ---- phase A (serial): all hops but the last, and the stream segmentation of the last hop
+  {
+    std::vector<int32_t>& pos = S->pos[0];
+    for (int32_t c = 0; c < n_class; ++c) {
+      ClassOut& C = co[(size_t)c];
+      const bool keep = materialise == nullptr || materialise[c] != 0;
+      keepv[(size_t)c] = keep;
+      C.level_count.assign((size_t)nh + 1, 0);
+      C.hop.resize((size_t)nh);
+      C.nid.clear();
+      for (int64_t t = batch_off[c]; t < batch_off[c + 1]; ++t) {
+        const int32_t v = (int32_t)batch[t];
+        if (v < 0 || v >= S->n) return GS_EINVAL;
+        pos[(size_t)v] = (int32_t)C.nid.size();
+        C.nid.push_back(v);
       }
-      const int32_t col_base = keep ? seg[h + 1][c] : 0;
-      for (int32_t t = 0; t < n_rows; ++t) {
-        const int32_t v = nid[t];
-        const int64_t beg = rp[v], deg = rp[v + 1] - beg;
-        std::unordered_set<int64_t> chosen;
-        if (deg <= k) {
-          for (int64_t j = 0; j < deg; ++j) chosen.insert(j);
-        } else {
-          for (int64_t j = deg - k; j < deg; ++j) {
-            const int64_t r = (int64_t)(rng() % (uint32_t)j);
-            if (!chosen.insert(r).second) chosen.insert(j);
-          }
-        }
-        rowbuf.clear();
-        for (const int64_t& p : chosen) {
-          const int64_t e = beg + p;
-          const int32_t u = gc[e];
-          int32_t loc = S->pos[u];
-          if (loc < 0) {
-            loc = (int32_t)nid.size();
-            S->pos[u] = loc;
-            nid.push_back(u);
-          }
-          rowbuf.push_back(Entry{loc, e});
-        }
-        if (keep) {
-          std::sort(rowbuf.begin(), rowbuf.end(), [](const Entry& a, const Entry& b) { return a.local < b.local; });
-          Blk& B = blk[h];
-          for (const Entry& en : rowbuf) {
-            B.col.push_back(col_base + en.local);
-            B.val.push_back(gv[en.e]);
-            if (last) B.gcol.push_back(gc[en.e]);
-          }
-          B.rowptr.push_back((int32_t)B.col.size());
-        }
+      C.level_count[0] = (int32_t)C.nid.size();
+      for (int h = 0; h + 1 < nh; ++h) {
+        sample_hop(S, pos, rng, C.nid, S->fan[h], false, keep ? &C.hop[(size_t)h] : nullptr);
+        C.level_count[(size_t)h + 1] = (int32_t)C.nid.size();
       }
-      level_count[h + 1] = (int32_t)nid.size();
+      for (int32_t v : C.nid) pos[(size_t)v] = -1;
+      snap[(size_t)c] = rng;
+      rng.discard(count_draws(S, C.nid, S->fan[nh - 1]));
     }
-    for (int32_t v : nid) S->pos[v] = -1;
-    if (keep) {
-      const int32_t bsz = level_count[0];
-      for (int32_t t = 0; t < bsz; ++t) {
-        tcls.push_back(c);
-        inv_b.push_back(1.0f / (float)bsz);
-        target_ids.push_back(nid[t]);
-      }
-      nid_all.insert(nid_all.end(), nid.begin(), nid.end());
-    }
-    for (int l = 0; l <= nh; ++l) seg[l][c + 1] = seg[l][c] + (keep ? level_count[l] : 0);
   }
+  std::memcpy(mt_state, rng.s, sizeof(rng.s));
   *mt_left = rng.left;
   *mt_next = rng.next;
 
-  // ---- pack -------------------------------------------------------------------------------
+  // ---- phase B (parallel over classes): the last hop, each class on its own segment of the stream
+  {
+    std::atomic<int32_t> next_class{0};
+    auto work = [&](int w) {
+      std::vector<int32_t>& pos = S->pos[(size_t)w];
+      if ((int32_t)pos.size() != S->n) pos.assign((size_t)S->n, -1);
+      for (;;) {
+        const int32_t c = next_class.fetch_add(1);
+        if (c >= n_class) break;
+        if (!keepv[(size_t)c]) continue;
+        ClassOut& C = co[(size_t)c];
+        for (size_t i = 0; i < C.nid.size(); ++i) pos[(size_t)C.nid[i]] = (int32_t)i;
+        Mt19937 local = snap[(size_t)c];
+        sample_hop(S, pos, local, C.nid, S->fan[nh - 1], true, &C.hop[(size_t)nh - 1]);
+        C.level_count[(size_t)nh] = (int32_t)C.nid.size();
+        for (int32_t v : C.nid) pos[(size_t)v] = -1;
+      }
+    };
+    int n_keep = 0;
+    for (int32_t c = 0; c < n_class; ++c) n_keep += keepv[(size_t)c];
+    const int nw = std::max(1, std::min(S->n_workers, n_keep));
+    if (nw == 1) {
+      work(0);
+    } else {
+      std::vector<std::thread> th;
+      for (int w = 1; w < nw; ++w) th.emplace_back(work, w);
+      work(0);
+      for (auto& t : th) t.join();
+    }
+  }
+
+  // ---- batch offsets
+  std::vector<std::vector<int32_t>> seg((size_t)nh + 1, std::vector<int32_t>((size_t)n_class + 1, 0));
+  for (int32_t c = 0; c < n_class; ++c)
+    for (int l = 0; l <= nh; ++l)
+      seg[(size_t)l][(size_t)c + 1] =
+          seg[(size_t)l][(size_t)c] + (keepv[(size_t)c] ? co[(size_t)c].level_count[(size_t)l] : 0);
+
+  // ---- pack ---------------------------------------------------------------------------------
   for (int i = 0; i < 64; ++i) desc[i] = -1;
   int64_t off = 0;
-  auto put = [&](const void* src, int64_t bytes) -> int64_t {
+  auto reserve = [&](int64_t bytes) -> int64_t {
     const int64_t at = off;
     if (at + bytes > out_cap) return -1;
-    if (bytes) std::memcpy(out + at, src, (size_t)bytes);
     off = align16(at + bytes);
     return at;
   };
   desc[0] = nh;
-  desc[1] = seg[0][n_class];
-  for (int l = 0; l <= nh; ++l) desc[2 + l] = seg[l][n_class];
+  desc[1] = seg[0][(size_t)n_class];
+  for (int l = 0; l <= nh; ++l) desc[2 + l] = seg[(size_t)l][(size_t)n_class];
+  const int64_t n_tgt = seg[0][(size_t)n_class], n_last = seg[(size_t)nh][(size_t)n_class];
   {
-    std::vector<int32_t> flat;
-    for (int l = 0; l <= nh; ++l) flat.insert(flat.end(), seg[l].begin(), seg[l].end());
-    if ((desc[8] = put(flat.data(), (int64_t)flat.size() * 4)) < 0) return GS_ENOSPC;
+    const int64_t bytes = (int64_t)(nh + 1) * (n_class + 1) * 4;
+    if ((desc[8] = reserve(bytes)) < 0) return GS_ENOSPC;
+    int32_t* d = reinterpret_cast<int32_t*>(out + desc[8]);
+    for (int l = 0; l <= nh; ++l)
+      std::memcpy(d + (size_t)l * (size_t)(n_class + 1), seg[(size_t)l].data(), (size_t)(n_class + 1) * 4);
   }
-  if ((desc[9] = put(nid_all.data(), (int64_t)nid_all.size() * 4)) < 0) return GS_ENOSPC;
-  if ((desc[10] = put(tcls.data(), (int64_t)tcls.size() * 4)) < 0) return GS_ENOSPC;
-  if ((desc[11] = put(inv_b.data(), (int64_t)inv_b.size() * 4)) < 0) return GS_ENOSPC;
-  if ((desc[12] = put(target_ids.data(), (int64_t)target_ids.size() * 4)) < 0) return GS_ENOSPC;
-  if (S->labels) {
-    std::vector<int32_t> tl(target_ids.size());
-    for (size_t i = 0; i < tl.size(); ++i) tl[i] = S->labels[target_ids[i]];
-    if ((desc[13] = put(tl.data(), (int64_t)tl.size() * 4)) < 0) return GS_ENOSPC;
-  }
-  std::vector<int32_t> t_rowptr, t_col, cursor;
-  std::vector<float> t_val;
-  for (int h = 0; h < nh; ++h) {
-    Blk& B = blk[h];
-    const int32_t n_rows = seg[h][n_class], n_cols = seg[h + 1][n_class];
-    const int64_t nnz = (int64_t)B.col.size();
-    if ((int32_t)B.rowptr.size() != n_rows + 1) return GS_EINVAL;
-    // transposed structure (sample-time CSC): deterministic, rows of A^T sorted by source row
-    t_rowptr.assign((size_t)n_cols + 1, 0);
-    for (int64_t e = 0; e < nnz; ++e) t_rowptr[(size_t)B.col[e] + 1]++;
-    for (int32_t j = 0; j < n_cols; ++j) t_rowptr[j + 1] += t_rowptr[j];
-    cursor.assign(t_rowptr.begin(), t_rowptr.end() - 1);
-    t_col.resize((size_t)nnz);
-    t_val.resize((size_t)nnz);
-    for (int32_t r = 0; r < n_rows; ++r)
-      for (int32_t e = B.rowptr[r]; e < B.rowptr[r + 1]; ++e) {
-        const int32_t w = cursor[B.col[e]]++;
-        t_col[w] = r;
-        t_val[w] = B.val[e];
+  if ((desc[9] = reserve(n_last * 4)) < 0) return GS_ENOSPC;
+  if ((desc[10] = reserve(n_tgt * 4)) < 0) return GS_ENOSPC;
+  if ((desc[11] = reserve(n_tgt * 4)) < 0) return GS_ENOSPC;
+  if ((desc[12] = reserve(n_tgt * 4)) < 0) return GS_ENOSPC;
+  if (S->labels && (desc[13] = reserve(n_tgt * 4)) < 0) return GS_ENOSPC;
+  {
+    int32_t* nid_all = reinterpret_cast<int32_t*>(out + desc[9]);
+    int32_t* tcls = reinterpret_cast<int32_t*>(out + desc[10]);
+    float* inv_b = reinterpret_cast<float*>(out + desc[11]);
+    int32_t* tgt = reinterpret_cast<int32_t*>(out + desc[12]);
+    int32_t* tlab = S->labels ? reinterpret_cast<int32_t*>(out + desc[13]) : nullptr;
+    for (int32_t c = 0; c < n_class; ++c) {
+      if (!keepv[(size_t)c]) continue;
+      const ClassOut& C = co[(size_t)c];
+      std::memcpy(nid_all + seg[(size_t)nh][(size_t)c], C.nid.data(), C.nid.size() * 4);
+      const int32_t bsz = C.level_count[0];
+      const int32_t o = seg[0][(size_t)c];
+      for (int32_t t = 0; t < bsz; ++t) {
+        tcls[o + t] = c;
+        inv_b[o + t] = 1.0f / (float)bsz;
+        tgt[o + t] = C.nid[(size_t)t];
+        if (tlab) tlab[o + t] = S->labels[C.nid[(size_t)t]];
       }
+    }
+  }
+  std::vector<int32_t> cursor;
+  for (int h = 0; h < nh; ++h) {
+    const int32_t n_rows = seg[(size_t)h][(size_t)n_class], n_cols = seg[(size_t)h + 1][(size_t)n_class];
+    int64_t nnz = 0;
+    for (int32_t c = 0; c < n_class; ++c)
+      if (keepv[(size_t)c]) nnz += (int64_t)co[(size_t)c].hop[(size_t)h].col.size();
     int64_t* d = desc + 16 + 8 * h;
     d[0] = nnz;
-    if ((d[1] = put(B.rowptr.data(), (int64_t)B.rowptr.size() * 4)) < 0) return GS_ENOSPC;
-    if ((d[2] = put(B.col.data(), nnz * 4)) < 0) return GS_ENOSPC;
-    if ((d[3] = put(B.val.data(), nnz * 4)) < 0) return GS_ENOSPC;
-    if ((d[4] = put(t_rowptr.data(), (int64_t)t_rowptr.size() * 4)) < 0) return GS_ENOSPC;
-    if ((d[5] = put(t_col.data(), nnz * 4)) < 0) return GS_ENOSPC;
-    if ((d[6] = put(t_val.data(), nnz * 4)) < 0) return GS_ENOSPC;
-    if (h == nh - 1) {
-      if ((d[7] = put(B.gcol.data(), nnz * 4)) < 0) return GS_ENOSPC;
+    if ((d[1] = reserve((int64_t)(n_rows + 1) * 4)) < 0) return GS_ENOSPC;
+    if ((d[2] = reserve(nnz * 4)) < 0) return GS_ENOSPC;
+    if ((d[3] = reserve(nnz * 4)) < 0) return GS_ENOSPC;
+    if ((d[4] = reserve((int64_t)(n_cols + 1) * 4)) < 0) return GS_ENOSPC;
+    if ((d[5] = reserve(nnz * 4)) < 0) return GS_ENOSPC;
+    if ((d[6] = reserve(nnz * 4)) < 0) return GS_ENOSPC;
+    if (h == nh - 1 && (d[7] = reserve(nnz * 4)) < 0) return GS_ENOSPC;
+    int32_t* rowptr = reinterpret_cast<int32_t*>(out + d[1]);
+    int32_t* col = reinterpret_cast<int32_t*>(out + d[2]);
+    float* val = reinterpret_cast<float*>(out + d[3]);
+    int32_t* t_rowptr = reinterpret_cast<int32_t*>(out + d[4]);
+    int32_t* t_col = reinterpret_cast<int32_t*>(out + d[5]);
+    float* t_val = reinterpret_cast<float*>(out + d[6]);
+    int32_t* gcol = (h == nh - 1) ? reinterpret_cast<int32_t*>(out + d[7]) : nullptr;
+    // forward structure: concatenate classes, shifting local columns by the class offset of the next level
+    int64_t e0 = 0;
+    rowptr[0] = 0;
+    for (int32_t c = 0; c < n_class; ++c) {
+      if (!keepv[(size_t)c]) continue;
+      const HopOut& H = co[(size_t)c].hop[(size_t)h];
+      const int32_t r0 = seg[(size_t)h][(size_t)c], cbase = seg[(size_t)h + 1][(size_t)c];
+      const int32_t rows_c = (int32_t)H.rowptr.size() - 1;
+      if (rows_c != co[(size_t)c].level_count[(size_t)h]) return GS_EINVAL;
+      for (int32_t r = 0; r < rows_c; ++r) rowptr[r0 + r + 1] = (int32_t)(e0 + H.rowptr[(size_t)r + 1]);
+      const size_t m = H.col.size();
+      for (size_t i = 0; i < m; ++i) col[e0 + (int64_t)i] = H.col[i] + cbase;
+      if (m) std::memcpy(val + e0, H.val.data(), m * 4);
+      if (gcol && m) std::memcpy(gcol + e0, H.gcol.data(), m * 4);
+      e0 += (int64_t)m;
     }
+    // transposed structure (sample-time CSC): deterministic, rows of A^T sorted by source row
+    std::memset(t_rowptr, 0, (size_t)(n_cols + 1) * 4);
+    for (int64_t e = 0; e < nnz; ++e) t_rowptr[col[e] + 1]++;
+    for (int32_t j = 0; j < n_cols; ++j) t_rowptr[j + 1] += t_rowptr[j];
+    cursor.assign(t_rowptr, t_rowptr + n_cols);
+    for (int32_t r = 0; r < n_rows; ++r)
+      for (int32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+        const int32_t w = cursor[(size_t)col[e]]++;
+        t_col[w] = r;
+        t_val[w] = val[e];
+      }
   }
   return off;
 }

@@ -7,6 +7,8 @@ checked out, advanced by the C++ sampler and written back, so both streams inter
 reference's.  Output arrays are packed into one pinned buffer and moved to HBM with a single copy.
 """
 import ctypes
+import queue
+import threading
 
 import numpy as np
 import torch
@@ -92,8 +94,9 @@ class ClassSampler:
         cap += 4 * lvl + 3 * 4 * rows + 16 * 8
         self.cap = int(cap)
         # ring of pinned staging buffers: a buffer is reused only after its H2D copy has completed
+        # (3 slots: one being filled by the prefetch worker, one queued, one being copied / consumed)
         self.ring = [torch.empty(self.cap, dtype=torch.uint8, pin_memory=self.device.type == "cuda")
-                     for _ in range(3 if self.device.type == "cuda" else 1)]
+                     for _ in range(3)]
         self.ring_events = [None] * len(self.ring)
         self.ring_pos = 0
         self.pinned = self.ring[0]
@@ -124,7 +127,8 @@ class ClassSampler:
         return np.concatenate(parts), off
 
     def sample_host(self, materialise=None):
-        """Runs the sampler; returns (bytes_used, desc copy).  The packed arrays are in self.pinned."""
+        """Runs the sampler; returns (bytes_used, desc copy).  The packed arrays are in self.pinned
+        (= self.ring[self.ring_pos]).  Safe to call from a worker thread: no CUDA work is issued here."""
         batch, off = self.draw_batches()
         self.ring_pos = (self.ring_pos + 1) % len(self.ring)
         if self.ring_events[self.ring_pos] is not None:
@@ -192,18 +196,72 @@ class ClassSampler:
             rb.seg = [segs[l][idx].contiguous() for l in range(nh + 1)]
         return rb
 
-    def sample(self, materialise=None):
-        """Full step: host sampling, one H2D copy of the packed bytes, device views."""
-        used, desc = self.sample_host(materialise)
+    def upload(self, slot, used, desc, materialise=None):
+        """One H2D copy of the packed bytes of ring slot `slot`, then device views."""
+        src = self.ring[slot]
         if self.device.type == "cuda":
             dev = torch.empty(used, dtype=torch.uint8, device=self.device)
-            dev.copy_(self.pinned[:used], non_blocking=True)
+            dev.copy_(src[:used], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
-            self.ring_events[self.ring_pos] = ev
+            self.ring_events[slot] = ev
         else:
-            dev = self.pinned[:used].clone()
+            dev = src[:used].clone()
         rb = self.unpack(dev, desc, materialise)
         rb.h2d_bytes = used
         self.bytes_moved += used
         return rb
+
+    def sample(self, materialise=None):
+        """Full step: host sampling, one H2D copy of the packed bytes, device views."""
+        used, desc = self.sample_host(materialise)
+        return self.upload(self.ring_pos, used, desc, materialise)
+
+    def prefetch(self, n_steps, materialise=None):
+        """Samples the next `n_steps` outer steps on a worker thread (the C++ sampler releases the GIL), at most one
+        step ahead of the consumer, so host sampling overlaps the GPU work of the previous step.  Both random streams
+        are consumed in exactly the order a synchronous loop would consume them; the caller must not touch numpy's /
+        torch's global generators until `join()`."""
+        return _Prefetcher(self, n_steps, materialise)
+
+
+class _Prefetcher:
+    def __init__(self, sampler, n_steps, materialise):
+        self.s, self.mat = sampler, materialise
+        self.q = queue.Queue(maxsize=1)
+        self.stop = False
+        self.thread = threading.Thread(target=self._run, args=(n_steps,), daemon=True)
+        self.thread.start()
+
+    def _run(self, n_steps):
+        try:
+            for _ in range(n_steps):
+                if self.stop:
+                    return
+                used, desc = self.s.sample_host(self.mat)
+                self._put((self.s.ring_pos, used, desc))
+        except BaseException as exc:           # surfaced by next()
+            self._put(exc)
+
+    def _put(self, item):
+        while not self.stop:
+            try:
+                self.q.put(item, timeout=0.05)
+                return
+            except queue.Full:
+                continue
+
+    def next(self):
+        item = self.q.get()
+        if isinstance(item, BaseException):
+            raise item
+        slot, used, desc = item
+        return self.s.upload(slot, used, desc, self.mat)
+
+    def join(self):
+        """Normal end of an epoch: every step has been consumed.  After an error in the consumer the worker is told to
+        stop (the random streams are then left mid-epoch, as they would be after the same error in a serial loop)."""
+        self.stop = not self.q.empty() or self.stop
+        if self.thread.is_alive() and self.q.full():
+            self.stop = True
+        self.thread.join(timeout=60)

@@ -187,6 +187,8 @@ gs_sampler* gs_sampler_create(int32_t n_nodes, const int64_t* rowptr, const int3
 void gs_sampler_destroy(gs_sampler* s);
 /* optional: int32 label per node; the labels of the target rows are then emitted with every step */
 void gs_sampler_set_labels(gs_sampler* s, const int32_t* labels);
+/* worker threads for the last (largest) hop; default = min(hardware threads, 16); results do not depend on it */
+void gs_sampler_set_threads(gs_sampler* s, int32_t n);
 /* batch: concatenated class batches (node ids), batch_off[n_class+1]; materialise[c] != 0 selects the classes
  * whose blocks are written (others only advance the generator).  out: packed buffer of `out_cap` bytes;
  * desc: int64[64] table describing where each array landed.  Returns bytes used or a negative code. */

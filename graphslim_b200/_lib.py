@@ -26,7 +26,8 @@ SIGNATURES = {
     "gs_gemm_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_int]),
     "gs_gemm_f32": (c_int, [c_int, c_int, c_i32, c_i32, c_i32, c_f32, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_i64,
                             c_int, c_vp, c_i64, c_vp]),
-    "gs_gemm_grouped_tn_f32": (c_int, [c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "gs_gemm_grouped_tn_f32": (c_int, [c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
+                                       c_int, c_vp, c_i64, c_vp]),
     "gs_bias_act_f32": (c_int, [c_i32, c_i32, c_vp, c_i64, c_vp, c_int, c_vp]),
     "gs_relu_mask_f32": (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "gs_softmax_residual_f32": (c_int, [c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -59,6 +60,7 @@ SIGNATURES = {
     "gs_sampler_destroy": (None, [c_vp]),
     "gs_sampler_set_labels": (None, [c_vp, c_vp]),
     "gs_sampler_set_threads": (None, [c_vp, c_i32]),
+    "gs_sampler_set_align": (None, [c_vp, c_i32]),
     "gs_sampler_sample_step": (c_i64, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
 }
 

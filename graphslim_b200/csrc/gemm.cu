@@ -15,6 +15,9 @@ int gemm_tc_dispatch(int ta, int tb, int M, int N, int K, float alpha, const flo
                      int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* workspace,
                      int64_t workspace_bytes, cudaStream_t st);
 int64_t gemm_tc_workspace_bytes(int M, int N, int K, int precision);
+int gemm_tc_grouped_dispatch(int G, const int32_t* seg, const int32_t* out_block, int M, int N, int K_total,
+                             const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                             int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
 struct GemmProblem {
   int ta, tb;
@@ -202,10 +205,15 @@ int64_t gs_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K, int precision) 
 }
 
 int gs_gemm_grouped_tn_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t M, int32_t N,
-                           const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
-                           void* stream) {
-  GS_REQUIRE(G >= 0 && seg && out_block && M >= 0 && N >= 0 && A && B && C && lda >= M && ldb >= N);
+                           int32_t K_total, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                           int64_t ldc, int precision, void* workspace, int64_t workspace_bytes, void* stream) {
+  GS_REQUIRE(G >= 0 && seg && out_block && M >= 0 && N >= 0 && K_total >= 0 && A && B && C && lda >= M && ldb >= N);
   if (G == 0 || M == 0 || N == 0) return GS_OK;
+  if (precision != 0) {
+    const int rc = gs::gemm_tc_grouped_dispatch(G, seg, out_block, M, N, K_total, A, lda, B, ldb, C, ldc, precision,
+                                                workspace, workspace_bytes, gs::as_stream(stream));
+    if (rc != GS_ENOSYS) return rc;
+  }
   gs::GemmProblem p{1, 0, M, N, 0, 1.f, 0.f, A, lda, B, ldb, C, ldc, 1, 0, seg, out_block};
   return gs::launch_simt(p, G, gs::as_stream(stream));
 }

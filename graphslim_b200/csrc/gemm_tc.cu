@@ -31,6 +31,8 @@
 // i+1; K can be split across CTAs (dW = dY^T H with K = N'^2 has only h*h outputs).
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gs {
@@ -57,7 +59,49 @@ struct Params {
   int splits;      // K split count (>1: epilogue uses atomics, C pre-scaled by the caller)
   int kchunk;      // K range per split (multiple of BK)
   int tiles_m, tiles_n;
+  // grouped mode (seg != nullptr): group g contracts rows seg[g]..seg[g+1] (64-aligned) of A (K x M) and B (K x N)
+  // into the column block out_block[g] of C; every group is split `splits` ways along K; C is pre-zeroed, atomics.
+  const int32_t* seg;
+  const int32_t* out_block;
+  int groups;
 };
+
+struct Tile {
+  int mb, nb, k_beg, k_end;
+  int64_t c_col;   // column offset of this tile's output block in C
+};
+
+// Work item -> tile coordinates; false when the item is empty (all three warp roles skip it identically).
+__device__ __forceinline__ bool decode_tile(const Params& p, int tile, Tile& t) {
+  const int ks = tile % p.splits;
+  int mn = tile / p.splits;
+  if (p.seg) {
+    const int per_group = p.tiles_m * p.tiles_n;
+    const int g = mn / per_group;
+    mn -= g * per_group;
+    const int kb = __ldg(p.seg + g), ke = __ldg(p.seg + g + 1);
+    const int nkb = (ke - kb + BK - 1) / BK;
+    const int chunk = ((nkb + p.splits - 1) / p.splits) * BK;
+    t.k_beg = kb + ks * chunk;
+    t.k_end = min(ke, t.k_beg + chunk);
+    t.c_col = (int64_t)__ldg(p.out_block + g) * p.N;
+  } else {
+    t.k_beg = ks * p.kchunk;
+    t.k_end = min(p.K, t.k_beg + p.kchunk);
+    t.c_col = 0;
+  }
+  t.mb = mn % p.tiles_m;
+  t.nb = mn / p.tiles_m;
+  return t.k_beg < t.k_end;
+}
+// first non-empty work item at or after `tile` (stride gridDim.x); false when the list is exhausted
+__device__ __forceinline__ bool seek_tile(const Params& p, int& tile, int num_tiles, Tile& t) {
+  while (tile < num_tiles) {
+    if (decode_tile(p, tile, t)) return true;
+    tile += gridDim.x;
+  }
+  return false;
+}
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -340,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
   __shared__ uint32_t tmem_holder;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n * p.splits;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.splits * (p.seg ? p.groups : 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -366,13 +410,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
     // flattened (tile, k-block) work list with a one-item register prefetch
     int tile = blockIdx.x;
     int k0 = 0, k_end = 0, mb = 0, nb = 0;
-    bool valid = tile < num_tiles;
+    Tile tl;
+    bool valid = seek_tile(p, tile, num_tiles, tl);
     if (valid) {
-      const int ks = tile % p.splits, mn = tile / p.splits;
-      mb = mn % p.tiles_m;
-      nb = mn / p.tiles_m;
-      k0 = ks * p.kchunk;
-      k_end = min(p.K, k0 + p.kchunk);
+      mb = tl.mb;
+      nb = tl.nb;
+      k0 = tl.k_beg;
+      k_end = tl.k_end;
     }
     TileRegs<BM> nxt;
     if (valid) {
@@ -387,13 +431,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
       k0 += BK;
       if (k0 >= k_end) {
         tile += gridDim.x;
-        valid = tile < num_tiles;
+        valid = seek_tile(p, tile, num_tiles, tl);
         if (valid) {
-          const int ks = tile % p.splits, mn = tile / p.splits;
-          mb = mn % p.tiles_m;
-          nb = mn / p.tiles_m;
-          k0 = ks * p.kchunk;
-          k_end = min(p.K, k0 + p.kchunk);
+          mb = tl.mb;
+          nb = tl.nb;
+          k0 = tl.k_beg;
+          k_end = tl.k_end;
         }
       }
       if (valid) {
@@ -421,9 +464,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
   } else if (warp == 8) {
     // ============================== MMA issuer ==============================
     uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int ks = tile % p.splits;
-      const int k_beg = ks * p.kchunk, k_end = min(p.K, k_beg + p.kchunk);
+    Tile tl;
+    for (int tile = blockIdx.x; seek_tile(p, tile, num_tiles, tl); tile += gridDim.x, ++tcount) {
+      const int k_beg = tl.k_beg, k_end = tl.k_end;
       const int acc = tcount & 1;
       const uint32_t acc_ph = (tcount >> 1) & 1;
       mbar_wait(smem_u32(&bar_tempty[acc]), acc_ph ^ 1);
@@ -463,9 +506,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
     // ============================== epilogue ==============================
     const int q = warp & 3;                                 // TMEM lane quarter owned by this warp
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int mn = tile / p.splits;
-      const int mb = mn % p.tiles_m, nb = mn / p.tiles_m;
+    Tile tl;
+    const bool use_atomics = p.splits > 1 || p.seg != nullptr;
+    for (int tile = blockIdx.x; seek_tile(p, tile, num_tiles, tl); tile += gridDim.x, ++tcount) {
+      const int mb = tl.mb, nb = tl.nb;
       const int acc = tcount & 1;
       const uint32_t acc_ph = (tcount >> 1) & 1;
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_ph);
@@ -488,9 +532,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
           for (int rr = 0; rr < 32; ++rr) {
             const int row = row_base + rr;
             if (row >= p.M) break;
-            float* c = p.C + (int64_t)row * p.ldc + gc;
+            float* c = p.C + (int64_t)row * p.ldc + tl.c_col + gc;
             const float v = p.alpha * st[rr * 33 + lane];
-            if (p.splits > 1) {
+            if (use_atomics) {
               atomicAdd(c, v);
             } else if (p.beta == 0.f) {
               *c = v;
@@ -564,25 +608,39 @@ static int launch(Params& p, void* workspace, int64_t workspace_bytes, cudaStrea
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + BN - 1) / BN;
   const int64_t mn_tiles = (int64_t)p.tiles_m * p.tiles_n;
-  // split K when the output tiles alone cannot occupy the SMs
-  int splits = 1;
   const int kblocks = (p.K + BK - 1) / BK;
-  if (mn_tiles < kNumSMs && kblocks >= 8) {
-    splits = (int)((kNumSMs + mn_tiles - 1) / mn_tiles);
-    if (splits > kblocks / 4) splits = kblocks / 4;
+  int64_t total;
+  if (p.seg) {
+    // grouped: C is pre-zeroed by the caller and accumulated with atomics; split every group along K until the
+    // work list covers the machine about twice (groups have similar K: class batches of <= 256 targets)
+    const int64_t base = mn_tiles * p.groups;
+    int splits = (int)((2 * kNumSMs + base - 1) / base);
+    const int avg_kb = std::max(1, kblocks / std::max(1, p.groups));
+    if (splits > avg_kb / 2) splits = avg_kb / 2;
     if (splits < 1) splits = 1;
+    p.splits = splits;
+    p.kchunk = 0;
+    total = base * splits;
+  } else {
+    // split K when the output tiles alone cannot occupy the SMs
+    int splits = 1;
+    if (mn_tiles < kNumSMs && kblocks >= 8) {
+      splits = (int)((kNumSMs + mn_tiles - 1) / mn_tiles);
+      if (splits > kblocks / 4) splits = kblocks / 4;
+      if (splits < 1) splits = 1;
+    }
+    int kchunk = ((kblocks + splits - 1) / splits) * BK;
+    splits = (p.K + kchunk - 1) / kchunk;
+    p.splits = splits;
+    p.kchunk = kchunk;
+    if (splits > 1) {
+      const int64_t n = (int64_t)p.M * p.N;
+      scale_matrix_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.M, p.N, p.C, p.ldc, p.beta);
+      const int rc = finish_launch("scale_matrix_tc");
+      if (rc) return rc;
+    }
+    total = mn_tiles * splits;
   }
-  int kchunk = ((kblocks + splits - 1) / splits) * BK;
-  splits = (p.K + kchunk - 1) / kchunk;
-  p.splits = splits;
-  p.kchunk = kchunk;
-  if (splits > 1) {
-    const int64_t n = (int64_t)p.M * p.N;
-    scale_matrix_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.M, p.N, p.C, p.ldc, p.beta);
-    const int rc = finish_launch("scale_matrix_tc");
-    if (rc) return rc;
-  }
-  const int64_t total = mn_tiles * splits;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
   gemm_tc_kernel<BN, NPASS><<<grid, kThreads, smem, st>>>(p);
   return finish_launch("gemm_tc");
@@ -609,9 +667,30 @@ int gemm_tc_dispatch(int ta, int tb, int M, int N, int K, float alpha, const flo
                      int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* workspace,
                      int64_t workspace_bytes, cudaStream_t st) {
   if (!gemm_tc_covers(M, N, K)) return GS_ENOSYS;
-  tc::Params p{ta, tb, M, N, K, alpha, beta, A, lda, B, ldb, nullptr, C, ldc, 1, K, 0, 0};
+  tc::Params p{ta, tb, M, N, K, alpha, beta, A, lda, B, ldb, nullptr, C, ldc, 1, K, 0, 0, nullptr, nullptr, 0};
   const bool three = precision == 1;
   // accumulator width: the widest tile that does not waste more than half of its columns
+  switch (tc_bn(N)) {
+    case 256:
+      return three ? tc::launch<256, 3>(p, workspace, workspace_bytes, st) : tc::launch<256, 1>(p, workspace, workspace_bytes, st);
+    case 128:
+      return three ? tc::launch<128, 3>(p, workspace, workspace_bytes, st) : tc::launch<128, 1>(p, workspace, workspace_bytes, st);
+    case 64:
+      return three ? tc::launch<64, 3>(p, workspace, workspace_bytes, st) : tc::launch<64, 1>(p, workspace, workspace_bytes, st);
+    default:
+      return three ? tc::launch<32, 3>(p, workspace, workspace_bytes, st) : tc::launch<32, 1>(p, workspace, workspace_bytes, st);
+  }
+}
+
+
+// Grouped K-segmented product on the tensor cores: C[:, out_block[g]*N ...] += A[seg[g]:seg[g+1]]^T B[seg[g]:seg[g+1]].
+// Requirements (checked by the caller): every seg[g] is a multiple of 64 (gs_sampler_set_align(64)), C zeroed.
+int gemm_tc_grouped_dispatch(int G, const int32_t* seg, const int32_t* out_block, int M, int N, int K_total,
+                             const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                             int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  if (!gemm_tc_covers(M, N, K_total) || M < 8) return GS_ENOSYS;
+  tc::Params p{1, 0, M, N, K_total, 1.f, 0.f, A, lda, B, ldb, nullptr, C, ldc, 1, K_total, 0, 0, seg, out_block, G};
+  const bool three = precision == 1;
   switch (tc_bn(N)) {
     case 256:
       return three ? tc::launch<256, 3>(p, workspace, workspace_bytes, st) : tc::launch<256, 1>(p, workspace, workspace_bytes, st);

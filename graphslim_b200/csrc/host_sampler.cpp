@@ -100,6 +100,7 @@ struct gs_sampler {
   const int32_t* labels = nullptr;
   std::vector<std::vector<int32_t>> pos;    // per worker: node -> class-local index, -1 when unseen
   int n_workers = 1;
+  int32_t align = 1;                        // every class segment of every level is padded to a multiple of this
 };
 
 namespace {
@@ -226,6 +227,10 @@ void gs_sampler_set_labels(gs_sampler* s, const int32_t* labels) {
   if (s) s->labels = labels;
 }
 
+void gs_sampler_set_align(gs_sampler* s, int32_t align) {
+  if (s && align >= 1) s->align = align;
+}
+
 void gs_sampler_set_threads(gs_sampler* s, int32_t n) {
   if (s && n >= 1) {
     s->n_workers = n > 64 ? 64 : n;
@@ -312,10 +317,14 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
 
   // ---- batch offsets
   std::vector<std::vector<int32_t>> seg((size_t)nh + 1, std::vector<int32_t>((size_t)n_class + 1, 0));
+  // (padded to S->align rows per class: pad rows carry no edges, zero loss weight and node id 0, so they contribute
+  //  nothing, but every class segment then starts on a tile boundary of the tensor-core grouped products)
+  const int32_t al = S->align;
   for (int32_t c = 0; c < n_class; ++c)
-    for (int l = 0; l <= nh; ++l)
-      seg[(size_t)l][(size_t)c + 1] =
-          seg[(size_t)l][(size_t)c] + (keepv[(size_t)c] ? co[(size_t)c].level_count[(size_t)l] : 0);
+    for (int l = 0; l <= nh; ++l) {
+      const int32_t cnt = keepv[(size_t)c] ? co[(size_t)c].level_count[(size_t)l] : 0;
+      seg[(size_t)l][(size_t)c + 1] = seg[(size_t)l][(size_t)c] + (cnt + al - 1) / al * al;
+    }
 
   // ---- pack ---------------------------------------------------------------------------------
   for (int i = 0; i < 64; ++i) desc[i] = -1;
@@ -342,6 +351,13 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
   if ((desc[11] = reserve(n_tgt * 4)) < 0) return GS_ENOSPC;
   if ((desc[12] = reserve(n_tgt * 4)) < 0) return GS_ENOSPC;
   if (S->labels && (desc[13] = reserve(n_tgt * 4)) < 0) return GS_ENOSPC;
+  if ((desc[14] = reserve((int64_t)(nh + 1) * n_class * 4)) < 0) return GS_ENOSPC;   // true (unpadded) counts
+  {
+    int32_t* cnt = reinterpret_cast<int32_t*>(out + desc[14]);
+    for (int l = 0; l <= nh; ++l)
+      for (int32_t c = 0; c < n_class; ++c)
+        cnt[(size_t)l * (size_t)n_class + (size_t)c] = keepv[(size_t)c] ? co[(size_t)c].level_count[(size_t)l] : 0;
+  }
   {
     int32_t* nid_all = reinterpret_cast<int32_t*>(out + desc[9]);
     int32_t* tcls = reinterpret_cast<int32_t*>(out + desc[10]);
@@ -351,7 +367,10 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
     for (int32_t c = 0; c < n_class; ++c) {
       if (!keepv[(size_t)c]) continue;
       const ClassOut& C = co[(size_t)c];
-      std::memcpy(nid_all + seg[(size_t)nh][(size_t)c], C.nid.data(), C.nid.size() * 4);
+      int32_t* dst = nid_all + seg[(size_t)nh][(size_t)c];
+      std::memcpy(dst, C.nid.data(), C.nid.size() * 4);
+      for (int32_t t = (int32_t)C.nid.size(); t < seg[(size_t)nh][(size_t)c + 1] - seg[(size_t)nh][(size_t)c]; ++t)
+        dst[t] = 0;
       const int32_t bsz = C.level_count[0];
       const int32_t o = seg[0][(size_t)c];
       for (int32_t t = 0; t < bsz; ++t) {
@@ -359,6 +378,12 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
         inv_b[o + t] = 1.0f / (float)bsz;
         tgt[o + t] = C.nid[(size_t)t];
         if (tlab) tlab[o + t] = S->labels[C.nid[(size_t)t]];
+      }
+      for (int32_t t = bsz; t < seg[0][(size_t)c + 1] - o; ++t) {     // pad targets: zero weight in the loss
+        tcls[o + t] = c;
+        inv_b[o + t] = 0.0f;
+        tgt[o + t] = 0;
+        if (tlab) tlab[o + t] = 0;
       }
     }
   }
@@ -395,6 +420,7 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
       if (rows_c != co[(size_t)c].level_count[(size_t)h]) return GS_EINVAL;
       for (int32_t r = 0; r < rows_c; ++r) rowptr[r0 + r + 1] = (int32_t)(e0 + H.rowptr[(size_t)r + 1]);
       const size_t m = H.col.size();
+      for (int32_t r = r0 + rows_c; r < seg[(size_t)h][(size_t)c + 1]; ++r) rowptr[r + 1] = (int32_t)(e0 + (int64_t)m);
       for (size_t i = 0; i < m; ++i) col[e0 + (int64_t)i] = H.col[i] + cbase;
       if (m) std::memcpy(val + e0, H.val.data(), m * 4);
       if (gcol && m) std::memcpy(gcol + e0, H.gcol.data(), m * 4);

@@ -14,7 +14,44 @@
 
 namespace gs {
 
-constexpr int kSlice = 2048;
+constexpr int kSlice = 512;        // rows per block in the column reductions
+constexpr int kRedThreads = 256;
+
+// Thread layout of the column reductions: thread = (column quad q, row lane rl); a thread walks rows
+// r0+rl, r0+rl+RL, ... of its slice with float4 loads, so a block keeps QUADS*RL*16 B * unroll in flight.
+struct RedLayout {
+  int quads, rl, q, lane_row;
+  bool active;
+};
+__device__ __forceinline__ RedLayout red_layout(int h) {
+  RedLayout L;
+  L.quads = h >> 2;
+  L.rl = kRedThreads / L.quads;
+  if (L.rl < 1) L.rl = 1;
+  L.q = threadIdx.x % L.quads;
+  L.lane_row = threadIdx.x / L.quads;
+  L.active = threadIdx.x < L.quads * L.rl && L.quads <= kRedThreads;
+  return L;
+}
+// sums `v` (NS float4 statistics per thread) over the row lanes of the block and adds them to work[stat][col] (fp64)
+template <int NS>
+__device__ __forceinline__ void red_commit(const RedLayout& L, int h, const float4 (&v)[NS], float* sm /* NS*256*4 */,
+                                           double* const (&dst)[NS]) {
+#pragma unroll
+  for (int s = 0; s < NS; ++s) reinterpret_cast<float4*>(sm)[s * kRedThreads + threadIdx.x] = v[s];
+  __syncthreads();
+  for (int k = threadIdx.x; k < h; k += kRedThreads) {
+    const int q = k >> 2, e = k & 3;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      float acc = 0.f;
+      for (int r = 0; r < L.rl; ++r) acc += sm[(s * kRedThreads + r * L.quads + q) * 4 + e];
+      atomicAdd(dst[s] + k, (double)acc);
+    }
+  }
+}
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 struct Chunks {
   int nchunk;
@@ -42,43 +79,42 @@ static inline unsigned slice_grid(int64_t rows, int nchunk) { return (unsigned)(
 // ------------------------------------------------------------------------------------------------
 // statistics of y[k,:] over chunks; SRC 0: y = Pa[j]+Pb[i] (layer 1), SRC 1: y = Y[k,:]
 template <int SRC>
-__global__ void col_stats_partial_kernel(int n, int h, const float* __restrict__ Pa, const float* __restrict__ Pb,
-                                         const float* __restrict__ Y, Chunks ch, double* __restrict__ work) {
+__global__ void __launch_bounds__(kRedThreads)
+col_stats_partial_kernel(int n, int h, const float* __restrict__ Pa, const float* __restrict__ Pb,
+                         const float* __restrict__ Y, Chunks ch, double* __restrict__ work) {
+  __shared__ __align__(16) float sm[2 * kRedThreads * 4];
   int64_t r0, r1;
   int c;
   if (!slice_of_block(ch, r0, r1, c)) return;
-  const int64_t f = ch.off[c];  // shift row
-  for (int k = threadIdx.x; k < h; k += blockDim.x) {
-    float shift;
+  const RedLayout L = red_layout(h);
+  const int64_t f = ch.off[c];  // shift row: keeps the running sums variance-sized
+  float4 acc[2] = {f4_zero(), f4_zero()};
+  if (L.active) {
+    const int k = L.q * 4;
+    float4 shift;
     if (SRC == 0) {
-      shift = Pa[(f % n) * h + k] + Pb[(f / n) * h + k];
+      const float4 a = ld4(Pa + (f % n) * h + k), b = ld4(Pb + (f / n) * h + k);
+      shift = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
     } else {
-      shift = Y[f * h + k];
+      shift = ld4(Y + f * h + k);
     }
-    float s1 = 0.f, s2 = 0.f;
-    if (SRC == 0) {
-      int64_t i = r0 / n, j = r0 % n;
-      float pb = Pb[i * h + k];
-      for (int64_t r = r0; r < r1; ++r) {
-        const float y = Pa[j * h + k] + pb - shift;
-        s1 += y;
-        s2 = fmaf(y, y, s2);
-        if (++j == n) {
-          j = 0;
-          ++i;
-          if (r + 1 < r1) pb = Pb[i * h + k];
-        }
+#pragma unroll 4
+    for (int64_t r = r0 + L.lane_row; r < r1; r += L.rl) {
+      float4 y;
+      if (SRC == 0) {
+        const float4 a = ld4(Pa + (r % n) * h + k), b = ld4(Pb + (r / n) * h + k);
+        y = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      } else {
+        y = ld4(Y + r * h + k);
       }
-    } else {
-      for (int64_t r = r0; r < r1; ++r) {
-        const float y = Y[r * h + k] - shift;
-        s1 += y;
-        s2 = fmaf(y, y, s2);
-      }
+      y.x -= shift.x; y.y -= shift.y; y.z -= shift.z; y.w -= shift.w;
+      acc[0].x += y.x; acc[0].y += y.y; acc[0].z += y.z; acc[0].w += y.w;
+      acc[1].x = fmaf(y.x, y.x, acc[1].x); acc[1].y = fmaf(y.y, y.y, acc[1].y);
+      acc[1].z = fmaf(y.z, y.z, acc[1].z); acc[1].w = fmaf(y.w, y.w, acc[1].w);
     }
-    atomicAdd(&work[((int64_t)c * 2 + 0) * h + k], (double)s1);
-    atomicAdd(&work[((int64_t)c * 2 + 1) * h + k], (double)s2);
   }
+  double* const dst[2] = {work + ((int64_t)c * 2 + 0) * h, work + ((int64_t)c * 2 + 1) * h};
+  red_commit<2>(L, h, acc, sm, dst);
 }
 
 template <int SRC>
@@ -132,7 +168,7 @@ __global__ void pge_l1_expand_kernel(int n, int h, const float* __restrict__ Pa,
   }
 }
 
-// E[r] = relu(bn2(Y2[r,:])) . w3 + b3, one warp per row
+// E[r] = relu(bn2(Y2[r,:])) . w3 + b3, one warp per row, float4 per lane
 __global__ void pge_l3_kernel(int64_t rows, int h, const float* __restrict__ Y2, Chunks ch, const float* __restrict__ mean,
                               const float* __restrict__ rstd, const float* __restrict__ gamma,
                               const float* __restrict__ beta, const float* __restrict__ w3, const float* __restrict__ b3,
@@ -140,17 +176,22 @@ __global__ void pge_l3_kernel(int64_t rows, int h, const float* __restrict__ Y2,
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float bias = b3[0];
   for (int64_t r = warp; r < rows; r += nwarps) {
     const int c = chunk_of(r, ch.nchunk, ch.off);
     const float* mu = mean + (int64_t)c * h;
     const float* rs = rstd + (int64_t)c * h;
     float acc = 0.f;
-    for (int k = lane; k < h; k += 32) {
-      const float yh = fmaf(gamma[k], (Y2[r * h + k] - mu[k]) * rs[k], beta[k]);
-      acc = fmaf(fmaxf(yh, 0.f), w3[k], acc);
+    for (int k = lane * 4; k < h; k += 128) {
+      const float4 y = ld4(Y2 + r * h + k), m = ld4(mu + k), s = ld4(rs + k), g = ld4(gamma + k), b = ld4(beta + k),
+                   w = ld4(w3 + k);
+      acc = fmaf(fmaxf(fmaf(g.x, (y.x - m.x) * s.x, b.x), 0.f), w.x, acc);
+      acc = fmaf(fmaxf(fmaf(g.y, (y.y - m.y) * s.y, b.y), 0.f), w.y, acc);
+      acc = fmaf(fmaxf(fmaf(g.z, (y.z - m.z) * s.z, b.z), 0.f), w.z, acc);
+      acc = fmaf(fmaxf(fmaf(g.w, (y.w - m.w) * s.w, b.w), 0.f), w.w, acc);
     }
     acc = warp_sum(acc);
-    if (lane == 0) E[r] = acc + b3[0];
+    if (lane == 0) E[r] = acc + bias;
   }
 }
 
@@ -178,32 +219,43 @@ __global__ void pge_symm_sigmoid_bwd_kernel(int n, const float* __restrict__ dA,
 
 // ------------------------------------------------------------------------------------------------
 // layer-3 + BN2 backward statistics.  work layout: [nchunk][2][h] (s1,s2) then [h] dw3 then [1] db3
-__global__ void pge_l3_bwd_partial_kernel(int h, const float* __restrict__ Y2, const float* __restrict__ dE, Chunks ch,
-                                          const float* __restrict__ mean, const float* __restrict__ rstd,
-                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                          const float* __restrict__ w3, double* __restrict__ work) {
+__global__ void __launch_bounds__(kRedThreads)
+pge_l3_bwd_partial_kernel(int h, const float* __restrict__ Y2, const float* __restrict__ dE, Chunks ch,
+                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const float* __restrict__ w3, double* __restrict__ work) {
+  __shared__ __align__(16) float sm[3 * kRedThreads * 4];
   int64_t r0, r1;
   int c;
   if (!slice_of_block(ch, r0, r1, c)) return;
+  const RedLayout L = red_layout(h);
   double* dw3 = work + (int64_t)ch.nchunk * 2 * h;
-  for (int k = threadIdx.x; k < h; k += blockDim.x) {
-    const float mu = mean[(int64_t)c * h + k], rs = rstd[(int64_t)c * h + k], g = gamma[k], b = beta[k], w = w3[k];
-    float s1 = 0.f, s2 = 0.f, sw = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
-      const float xh = (Y2[r * h + k] - mu) * rs;
-      const float yh = fmaf(g, xh, b);
-      const float de = dE[r];
-      if (yh > 0.f) {
-        const float d = de * w;
-        s1 += d;
-        s2 = fmaf(d, xh, s2);
-        sw = fmaf(de, yh, sw);
-      }
-    }
-    atomicAdd(&work[((int64_t)c * 2 + 0) * h + k], (double)s1);
-    atomicAdd(&work[((int64_t)c * 2 + 1) * h + k], (double)s2);
-    atomicAdd(&dw3[k], (double)sw);
+  float4 acc[3] = {f4_zero(), f4_zero(), f4_zero()};   // s1, s2, dw3
+  if (L.active) {
+    const int k = L.q * 4;
+    const float4 mu = ld4(mean + (int64_t)c * h + k), rs = ld4(rstd + (int64_t)c * h + k), g = ld4(gamma + k),
+                 b = ld4(beta + k), w = ld4(w3 + k);
+#pragma unroll 4
+    for (int64_t r = r0 + L.lane_row; r < r1; r += L.rl) {
+      const float4 y = ld4(Y2 + r * h + k);
+      const float de = __ldg(dE + r);
+#define GS_L3B(cmp)                                         \
+  {                                                         \
+    const float xh = (y.cmp - mu.cmp) * rs.cmp;             \
+    const float yh = fmaf(g.cmp, xh, b.cmp);                \
+    if (yh > 0.f) {                                         \
+      const float d = de * w.cmp;                           \
+      acc[0].cmp += d;                                      \
+      acc[1].cmp = fmaf(d, xh, acc[1].cmp);                 \
+      acc[2].cmp = fmaf(de, yh, acc[2].cmp);                \
+    }                                                       \
   }
+      GS_L3B(x) GS_L3B(y) GS_L3B(z) GS_L3B(w)
+#undef GS_L3B
+    }
+  }
+  double* const dst[3] = {work + ((int64_t)c * 2 + 0) * h, work + ((int64_t)c * 2 + 1) * h, dw3};
+  red_commit<3>(L, h, acc, sm, dst);
   if (threadIdx.x < 32) {
     float sb = 0.f;
     for (int64_t r = r0 + threadIdx.x; r < r1; r += 32) sb += dE[r];
@@ -263,34 +315,39 @@ __global__ void pge_bn2_bwd_apply_kernel(int64_t rows, int h, const float* __res
 
 // ------------------------------------------------------------------------------------------------
 // BN1 backward statistics from dH1; work layout [nchunk][2][h]
-__global__ void pge_bn1_bwd_partial_kernel(int n, int h, const float* __restrict__ dH1, const float* __restrict__ Pa,
-                                           const float* __restrict__ Pb, Chunks ch, const float* __restrict__ mean,
-                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                           const float* __restrict__ beta, double* __restrict__ work) {
+__global__ void __launch_bounds__(kRedThreads)
+pge_bn1_bwd_partial_kernel(int n, int h, const float* __restrict__ dH1, const float* __restrict__ Pa,
+                           const float* __restrict__ Pb, Chunks ch, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, double* __restrict__ work) {
+  __shared__ __align__(16) float sm[2 * kRedThreads * 4];
   int64_t r0, r1;
   int c;
   if (!slice_of_block(ch, r0, r1, c)) return;
-  for (int k = threadIdx.x; k < h; k += blockDim.x) {
-    const float mu = mean[(int64_t)c * h + k], rs = rstd[(int64_t)c * h + k], g = gamma[k], b = beta[k];
-    float s1 = 0.f, s2 = 0.f;
-    int64_t i = r0 / n, j = r0 % n;
-    float pb = Pb[i * h + k];
-    for (int64_t r = r0; r < r1; ++r) {
-      const float xh = (Pa[j * h + k] + pb - mu) * rs;
-      if (fmaf(g, xh, b) > 0.f) {
-        const float d = dH1[r * h + k];
-        s1 += d;
-        s2 = fmaf(d, xh, s2);
-      }
-      if (++j == n) {
-        j = 0;
-        ++i;
-        if (r + 1 < r1) pb = Pb[i * h + k];
-      }
-    }
-    atomicAdd(&work[((int64_t)c * 2 + 0) * h + k], (double)s1);
-    atomicAdd(&work[((int64_t)c * 2 + 1) * h + k], (double)s2);
+  const RedLayout L = red_layout(h);
+  float4 acc[2] = {f4_zero(), f4_zero()};
+  if (L.active) {
+    const int k = L.q * 4;
+    const float4 mu = ld4(mean + (int64_t)c * h + k), rs = ld4(rstd + (int64_t)c * h + k), g = ld4(gamma + k),
+                 b = ld4(beta + k);
+#pragma unroll 4
+    for (int64_t r = r0 + L.lane_row; r < r1; r += L.rl) {
+      const float4 d = ld4(dH1 + r * h + k);
+      const float4 pa = ld4(Pa + (r % n) * h + k), pb = ld4(Pb + (r / n) * h + k);
+#define GS_B1(cmp)                                            \
+  {                                                           \
+    const float xh = (pa.cmp + pb.cmp - mu.cmp) * rs.cmp;     \
+    if (fmaf(g.cmp, xh, b.cmp) > 0.f) {                       \
+      acc[0].cmp += d.cmp;                                    \
+      acc[1].cmp = fmaf(d.cmp, xh, acc[1].cmp);               \
+    }                                                         \
   }
+      GS_B1(x) GS_B1(y) GS_B1(z) GS_B1(w)
+#undef GS_B1
+    }
+  }
+  double* const dst[2] = {work + ((int64_t)c * 2 + 0) * h, work + ((int64_t)c * 2 + 1) * h};
+  red_commit<2>(L, h, acc, sm, dst);
 }
 
 __global__ void cast_f64_f32_2_kernel(int cnt, int h, const double* __restrict__ work, float* __restrict__ s1,
@@ -304,42 +361,60 @@ __global__ void cast_f64_f32_2_kernel(int cnt, int h, const double* __restrict__
 
 // blockIdx.x < n : i = blockIdx.x, dPb[i,:] = sum_j dY1[i,j,:]
 // blockIdx.x >= n: j = blockIdx.x - n, dPa[j,:] = sum_i dY1[i,j,:]
-__global__ void pge_bn1_bwd_reduce_kernel(int n, int h, const float* __restrict__ dH1, const float* __restrict__ Pa,
-                                          const float* __restrict__ Pb, Chunks ch, const float* __restrict__ mean,
-                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                          const float* __restrict__ beta, const float* __restrict__ s1,
-                                          const float* __restrict__ s2, float* __restrict__ dPa,
-                                          float* __restrict__ dPb) {
+// thread = (column quad, row lane): the n summands are split over the row lanes and combined through smem.
+__global__ void __launch_bounds__(kRedThreads)
+pge_bn1_bwd_reduce_kernel(int n, int h, const float* __restrict__ dH1, const float* __restrict__ Pa,
+                          const float* __restrict__ Pb, Chunks ch, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const float* __restrict__ s1, const float* __restrict__ s2,
+                          float* __restrict__ dPa, float* __restrict__ dPb) {
+  __shared__ __align__(16) float sm[kRedThreads * 4];
   const bool row_mode = blockIdx.x < (unsigned)n;
   const int fixed = row_mode ? blockIdx.x : blockIdx.x - n;
-  for (int k = threadIdx.x; k < h; k += blockDim.x) {
-    const float g = gamma[k], b = beta[k];
-    const float pf = row_mode ? Pb[(int64_t)fixed * h + k] : Pa[(int64_t)fixed * h + k];
-    float acc = 0.f;
+  const RedLayout L = red_layout(h);
+  float4 acc = f4_zero();
+  if (L.active) {
+    const int k = L.q * 4;
+    const float4 g = ld4(gamma + k), b = ld4(beta + k);
+    const float4 pf = ld4((row_mode ? Pb : Pa) + (int64_t)fixed * h + k);
     int c = -1;
-    int64_t c_end = -1;
-    float mu = 0.f, rs = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int t = 0; t < n; ++t) {
+    int64_t c_beg = 0, c_end = -1;
+    float4 mu = f4_zero(), rs = f4_zero(), a1 = f4_zero(), a2 = f4_zero();
+#pragma unroll 2
+    for (int t = L.lane_row; t < n; t += L.rl) {
       const int64_t r = row_mode ? (int64_t)fixed * n + t : (int64_t)t * n + fixed;
-      if (r >= c_end || c < 0 || r < ch.off[c]) {
+      if (c < 0 || r >= c_end || r < c_beg) {
         c = chunk_of(r, ch.nchunk, ch.off);
+        c_beg = ch.off[c];
         c_end = ch.off[c + 1];
-        const float inv_m = 1.f / (float)(ch.off[c + 1] - ch.off[c]);
-        mu = mean[(int64_t)c * h + k];
-        rs = rstd[(int64_t)c * h + k];
-        a1 = s1[(int64_t)c * h + k] * inv_m;
-        a2 = s2[(int64_t)c * h + k] * inv_m;
+        const float inv_m = 1.f / (float)(c_end - c_beg);
+        mu = ld4(mean + (int64_t)c * h + k);
+        rs = ld4(rstd + (int64_t)c * h + k);
+        a1 = ld4(s1 + (int64_t)c * h + k);
+        a2 = ld4(s2 + (int64_t)c * h + k);
+        a1.x *= inv_m; a1.y *= inv_m; a1.z *= inv_m; a1.w *= inv_m;
+        a2.x *= inv_m; a2.y *= inv_m; a2.z *= inv_m; a2.w *= inv_m;
       }
-      const float po = row_mode ? Pa[(int64_t)t * h + k] : Pb[(int64_t)t * h + k];
-      const float xh = (pf + po - mu) * rs;
-      const float d = (fmaf(g, xh, b) > 0.f) ? dH1[r * h + k] : 0.f;
-      acc += g * rs * (d - a1 - xh * a2);
+      const float4 po = ld4((row_mode ? Pa : Pb) + (int64_t)t * h + k);
+      const float4 d = ld4(dH1 + r * h + k);
+#define GS_B1R(cmp)                                                            \
+  {                                                                            \
+    const float xh = (pf.cmp + po.cmp - mu.cmp) * rs.cmp;                      \
+    const float dd = (fmaf(g.cmp, xh, b.cmp) > 0.f) ? d.cmp : 0.f;             \
+    acc.cmp += g.cmp * rs.cmp * (dd - a1.cmp - xh * a2.cmp);                   \
+  }
+      GS_B1R(x) GS_B1R(y) GS_B1R(z) GS_B1R(w)
+#undef GS_B1R
     }
-    if (row_mode) {
-      dPb[(int64_t)fixed * h + k] = acc;
-    } else {
-      dPa[(int64_t)fixed * h + k] = acc;
-    }
+  }
+  reinterpret_cast<float4*>(sm)[threadIdx.x] = acc;
+  __syncthreads();
+  float* out = (row_mode ? dPb : dPa) + (int64_t)fixed * h;
+  for (int k = threadIdx.x; k < h; k += kRedThreads) {
+    const int q = k >> 2, e = k & 3;
+    float v = 0.f;
+    for (int r = 0; r < L.rl; ++r) v += sm[(r * L.quads + q) * 4 + e];
+    out[k] = v;
   }
 }
 
@@ -348,7 +423,7 @@ __global__ void pge_bn1_bwd_reduce_kernel(int n, int h, const float* __restrict_
 extern "C" {
 using namespace gs;
 
-#define GS_PGE_COMMON_REQ GS_REQUIRE(nchunk >= 1 && nchunk <= 16 && chunk_off && h > 0 && h % 4 == 0)
+#define GS_PGE_COMMON_REQ GS_REQUIRE(nchunk >= 1 && nchunk <= 16 && chunk_off && h > 0 && h % 4 == 0 && h <= 1024)
 
 int gs_pge_l1_stats_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, int32_t nchunk, const int64_t* chunk_off,
                         float eps, float* mean, float* rstd, double* work, void* stream) {

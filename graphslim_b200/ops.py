@@ -135,14 +135,22 @@ class CudaOps:
             self._ws = ws
         return ws
 
-    def gemm_grouped_tn(self, A, B, seg, out_block, nblk):
-        """out[:, out_block[g]*N:(out_block[g]+1)*N] = A[seg[g]:seg[g+1]]^T @ B[seg[g]:seg[g+1]]; other blocks zero."""
+    def gemm_grouped_tn(self, A, B, seg, out_block, nblk, aligned=False, precision=None):
+        """out[:, out_block[g]*N:(out_block[g]+1)*N] = A[seg[g]:seg[g+1]]^T @ B[seg[g]:seg[g+1]]; other blocks zero.
+        aligned=True promises 64-row-aligned segments (the sampler's padding), which lets the product run on tcgen05."""
         lda, ldb = _mat(A, "A"), _mat(B, "B")
-        M, N = A.shape[1], B.shape[1]
+        M, N, Kt = A.shape[1], B.shape[1], A.shape[0]
         G = seg.numel() - 1
-        out = self.zeros(M, nblk * N) if G < nblk else self.empty(M, nblk * N)
-        _lib.check(self.lib.gs_gemm_grouped_tn_f32(G, _ptr(seg), _ptr(out_block), M, N, _ptr(A), lda, _ptr(B), ldb,
-                                                   _ptr(out), nblk * N, self.stream), "gs_gemm_grouped_tn_f32")
+        prec = (self.precision if precision is None else precision) if aligned else 0
+        ws, ws_bytes = None, 0
+        if prec:
+            ws_bytes = int(self.lib.gs_gemm_workspace_bytes(M, N, Kt, prec))
+            if ws_bytes:
+                ws = self._gemm_workspace(ws_bytes)
+        out = self.zeros(M, nblk * N) if (G < nblk or prec) else self.empty(M, nblk * N)
+        _lib.check(self.lib.gs_gemm_grouped_tn_f32(G, _ptr(seg), _ptr(out_block), M, N, Kt, _ptr(A), lda, _ptr(B), ldb,
+                                                   _ptr(out), nblk * N, prec, _ptr(ws), ws_bytes, self.stream),
+                   "gs_gemm_grouped_tn_f32")
         return out
 
     # -- sparse --------------------------------------------------------------------------------

@@ -65,7 +65,7 @@ class RealBatch:
 
 
 class ClassSampler:
-    def __init__(self, adj_rowptr, adj_col, adj_val, members, dataset, nlayers, device, batch=256):
+    def __init__(self, adj_rowptr, adj_col, adj_val, members, dataset, nlayers, device, batch=256, align=64):
         """adj_*: CSR of the normalised graph on the host (int64 rowptr, int32 col, fp32 val);
         members[c]: node ids of class c (global ids in 'trans', train-local in 'ind')."""
         self.lib = _lib.load()
@@ -83,15 +83,18 @@ class ClassSampler:
                                                  self.val.ctypes.data, self.nh, self.fan.ctypes.data)
         if not self.handle:
             raise _lib.GraphSlimLibraryError("gs_sampler_create failed")
-        # worst-case packed size
-        rows = min(batch, max(len(m) for m in self.members)) * self.n_class
+        self.align = int(align)
+        self.lib.gs_sampler_set_align(self.handle, self.align)
+        # worst-case packed size (every class segment padded to `align` rows at every level)
+        pad = lambda x: (x + self.align - 1) // self.align * self.align
+        rows = pad(min(batch, max(len(m) for m in self.members))) * self.n_class
         cap, lvl = 0, rows
         cap += 4 * (self.nh + 1) * (self.n_class + 1) + 64
         for k in self.fan:
             nnz = lvl * int(k)
-            cap += 4 * (lvl + 1) + 7 * 4 * nnz + 4 * (lvl + nnz + 1) + 8 * 16
-            lvl = lvl + nnz
-        cap += 4 * lvl + 3 * 4 * rows + 16 * 8
+            cap += 4 * (lvl + 1) + 7 * 4 * nnz + 4 * (lvl + nnz + self.align * self.n_class + 1) + 8 * 16
+            lvl = lvl + nnz + self.align * self.n_class
+        cap += 4 * lvl + 4 * 4 * rows + 4 * (self.nh + 1) * self.n_class + 16 * 8
         self.cap = int(cap)
         # ring of pinned staging buffers: a buffer is reused only after its H2D copy has completed
         # (3 slots: one being filled by the prefetch worker, one queued, one being copied / consumed)
@@ -164,6 +167,8 @@ class ClassSampler:
         rb.inv_b = self._view(buf, int(desc[11]), counts[0], torch.float32)
         rb.target_ids = self._view(buf, int(desc[12]), counts[0], torch.int32)
         rb.labels = self._view(buf, int(desc[13]), counts[0], torch.int32) if desc[13] >= 0 else None
+        rb.aligned = self.align % 64 == 0      # class segments start on tensor-core tile boundaries
+        rb.cnt = self._view(buf, int(desc[14]), (nh + 1) * nc, torch.int32).view(nh + 1, nc)   # unpadded class sizes
         blocks = []
         for h in range(nh):
             d = desc[16 + 8 * h: 24 + 8 * h]

@@ -81,10 +81,13 @@ int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, co
 
 /* Grouped K-segmented product for per-class weight gradients:
  * C[:, out_block[g]*N : (out_block[g]+1)*N] = A[seg[g]:seg[g+1], :M]^T * B[seg[g]:seg[g+1], :N]
- * (autograd.grad w.r.t. layer weights, one class per group; condensation/gcond_base.py:223,234) */
+ * (autograd.grad w.r.t. layer weights, one class per group; condensation/gcond_base.py:223,234).
+ * K_total = rows of A and B.  precision 0: fp32 SIMT, C is overwritten.  precision 1/2: tcgen05; requires every
+ * seg[g] to be a multiple of 64 (gs_sampler_set_align) and C zero-initialised by the caller (atomic accumulation);
+ * workspace as for gs_gemm_f32 with (M, N, K_total).                                                         */
 int gs_gemm_grouped_tn_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t M, int32_t N,
-                           const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
-                           void* stream);
+                           int32_t K_total, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                           int64_t ldc, int precision, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- small fused kernels of the condense model ------------------------------------------- */
 /* Z[r,c] += bias[c]; optional ReLU (models/layers.py:48-51,378-381; models/sgc.py:41) */
@@ -187,6 +190,9 @@ gs_sampler* gs_sampler_create(int32_t n_nodes, const int64_t* rowptr, const int3
 void gs_sampler_destroy(gs_sampler* s);
 /* optional: int32 label per node; the labels of the target rows are then emitted with every step */
 void gs_sampler_set_labels(gs_sampler* s, const int32_t* labels);
+/* pad every class segment of every level to a multiple of `align` rows (pad rows: no edges, zero loss weight);
+ * 64 makes the segments tile-aligned for the tensor-core grouped products */
+void gs_sampler_set_align(gs_sampler* s, int32_t align);
 /* worker threads for the last (largest) hop; default = min(hardware threads, 16); results do not depend on it */
 void gs_sampler_set_threads(gs_sampler* s, int32_t n);
 /* batch: concatenated class batches (node ids), batch_off[n_class+1]; materialise[c] != 0 selects the classes

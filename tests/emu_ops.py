@@ -44,7 +44,7 @@ class EmuOps:
             out.mul_(beta).add_(r)
         return out
 
-    def gemm_grouped_tn(self, A, B, seg, out_block, nblk):
+    def gemm_grouped_tn(self, A, B, seg, out_block, nblk, aligned=False, precision=None):
         M, N = A.shape[1], B.shape[1]
         out = torch.zeros(M, nblk * N, device=self.device)
         seg = seg.tolist()

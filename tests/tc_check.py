@@ -49,6 +49,24 @@ def run(mode):
             if not err < tol:
                 print("FAIL", flush=True)
                 return 1
+    # grouped K-segmented product (per-class weight gradients) with 64-aligned, partly empty segments
+    seg = torch.tensor([0, 640, 640, 6400, 6464, 13120], dtype=torch.int32)
+    ob = torch.tensor([3, 0, 1, 4, 2], dtype=torch.int32)
+    for (M, N) in ((128, 256), (256, 40), (602, 41)):
+        A = torch.randn(13120, M, generator=gen)
+        B = torch.randn(13120, N, generator=gen)
+        ref = torch.zeros(M, 6 * N, dtype=torch.float64)
+        sl = seg.tolist()
+        for g, o in enumerate(ob.tolist()):
+            ref[:, o * N:(o + 1) * N] = A[sl[g]:sl[g + 1]].double().T @ B[sl[g]:sl[g + 1]].double()
+        for prec in (1, 2):
+            out = K.gemm_grouped_tn(A.cuda(), B.cuda(), seg.cuda(), ob.cuda(), 6, aligned=True, precision=prec)
+            torch.cuda.synchronize()
+            err = (out.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+            print(f"grouped M={M} N={N} precision={prec}: max err / max|C| = {err:.3e}", flush=True)
+            if not err < (2e-5 if prec == 1 else 2e-2):
+                print("FAIL", flush=True)
+                return 1
     print(f"worst: 3xBF16 {worst[1]:.3e}, BF16 {worst[2]:.3e}")
     if mode == "bench":
         n, h = 909, 256

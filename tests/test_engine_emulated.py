@@ -29,7 +29,9 @@ def _digest(*arrays):
 def split_batch(rb, n_class):
     """Batched RealBatch -> per class (bs, n_id, [(rowptr, col, val) outermost hop first]) in reference conventions."""
     nh = len(rb.blocks)
-    seg = [s.cpu().numpy().astype(np.int64) for s in rb.seg]
+    seg = [s.cpu().numpy().astype(np.int64) for s in rb.seg]            # padded offsets of the groups
+    groups = rb.class_ids.cpu().numpy()
+    cnt = rb.cnt.cpu().numpy().astype(np.int64)[:, groups]              # true sizes of the groups
     out = []
     nid = rb.nid.cpu().numpy().astype(np.int64)
     for c in range(n_class):
@@ -37,11 +39,11 @@ def split_batch(rb, n_class):
         for h in reversed(range(nh)):
             csr = rb.blocks[h].csr
             rp = csr.rowptr.cpu().numpy().astype(np.int64)
-            r0, r1 = seg[h][c], seg[h][c + 1]
+            r0, r1 = seg[h][c], seg[h][c] + cnt[h][c]
             e0, e1 = rp[r0], rp[r1]
             blocks.append((rp[r0:r1 + 1] - e0, csr.col.cpu().numpy().astype(np.int64)[e0:e1] - seg[h + 1][c],
                            csr.val.cpu().numpy()[e0:e1]))
-        out.append((int(seg[0][c + 1] - seg[0][c]), nid[seg[nh][c]:seg[nh][c + 1]], blocks))
+        out.append((int(cnt[0][c]), nid[seg[nh][c]:seg[nh][c] + cnt[nh][c]], blocks))
     return out
 
 

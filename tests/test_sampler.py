@@ -47,7 +47,7 @@ def test_sampler_matches_oracle_bit_exact(dataset, nlayers):
             assert np.array_equal(nid_got, n_id)
             for (a, b, v), (a2, b2, v2) in zip(blocks[::-1], blocks_got):
                 assert np.array_equal(a, a2) and np.array_equal(b, b2) and np.array_equal(v, v2)
-            lab = rb.labels.numpy()[rb.seg[0][c]:rb.seg[0][c + 1]]
+            lab = rb.labels.numpy()[rb.seg[0][c]:rb.seg[0][c] + rb.cnt[0][c]]
             assert np.array_equal(lab, raw.y.numpy()[batch])
         assert end_np == np.random.randint(1 << 30) and end_t == int(torch.randint(0, 1 << 30, (1,)))
 
@@ -106,4 +106,5 @@ def test_empty_and_tiny_classes():
     np.random.seed(0)
     torch.manual_seed(0)
     rb = s.sample()
-    assert int(rb.seg[0][1]) == 1
+    assert int(rb.cnt[0][0]) == 1 and int(rb.seg[0][1]) == 64
+    assert float(rb.inv_b[0]) == 1.0 and float(rb.inv_b[1:64].abs().max()) == 0.0   # pad targets carry no weight

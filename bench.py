@@ -237,6 +237,7 @@ def run_ours(ns):
     lib.gs_launch_count_reset()
     h2d0 = getattr(agent.sampler, "bytes_moved", 0)
     agent.K.start_timing()
+    agent.host_wait_sampler_s = 0.0
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0.record()
@@ -246,6 +247,7 @@ def run_ours(ns):
     torch.cuda.synchronize()
     kernel_times = agent.K.stop_timing()
     launches = int(lib.gs_launch_count())
+    host_wait_sampler = getattr(agent, "host_wait_sampler_s", 0.0)
     if world > 1:
         dist.barrier()
     ms = t0.elapsed_time(t1)
@@ -319,6 +321,10 @@ def run_ours(ns):
                          "arxiv shape) and freshly sampled blocks through HBM; no explicit flush needed",
                    "sampled_block_bytes_per_epoch": int(sample_bytes_per_epoch)},
         "roofline": roof, "spmm": spmm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+        # device time of each phase of the epoch as a fraction of the timed region (CUDA events on the launch stream),
+        # and the host time the main thread spent waiting for the sampler worker
+        "phases": {k[6:]: round(v[1] / ms, 4) for k, v in sorted(kernel_times.items()) if k.startswith("phase_")},
+        "host_wait_sampler_frac": round(host_wait_sampler * 1e3 / ms, 4),
     }
     print(json.dumps(line))
 

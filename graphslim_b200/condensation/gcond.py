@@ -37,6 +37,7 @@ class GCond(GCondBase):
             self.adj_syn = torch.eye(self.nnodes_syn, device=K.device)      # gcondx.py:32
         self.loss_avg, self.best_val = 0, 0
         self.adj_syn_inner = None
+        self._pge_ready = None
         self._loss_dev = K.zeros(1)
 
     def run_epoch(self, it):
@@ -66,31 +67,44 @@ class GCond(GCondBase):
         args, K, pge, model = self.args, self.K, self.pge, self.model
         for ol in range(outer_loop):
             if not self.x_variant:
-                adj_raw = pge.forward(self.feat_syn)
-                self.adj_syn, r_norm = K.dense_gcn_norm(adj_raw)
+                with K.timed("phase_pge_forward"):
+                    if self._pge_ready is None:
+                        adj_raw = pge.forward(self.feat_syn)
+                        self.adj_syn, r_norm = K.dense_gcn_norm(adj_raw)
+                    else:
+                        # the previous step's pge.inference(feat_syn) computed exactly this forward (same parameters,
+                        # same features, same batch statistics); its activations were kept for the backward below
+                        self.adj_syn, r_norm = self._pge_ready
+                        self._pge_ready = None
             loss, dX, dA, rb = self.match_step(model)
-            loss, dX, dA = self.reduce_partials(loss, dX, dA)     # class sharding: one all-reduce per outer step
+            with K.timed("phase_allreduce"):
+                loss, dX, dA = self.reduce_partials(loss, dX, dA)     # class sharding: one all-reduce per outer step
             K.axpby(1.0, loss, 1.0, self._loss_dev)
             if self.x_variant:
                 pge_grads, feat_grad = None, dX
             else:
-                dA_raw = K.dense_gcn_norm_bwd(dA, self.adj_syn, r_norm)
-                pge_grads, dX_pge = pge.backward(dA_raw)
-                feat_grad = K.axpby(1.0, dX_pge, 1.0, dX)
+                with K.timed("phase_pge_backward"):
+                    dA_raw = K.dense_gcn_norm_bwd(dA, self.adj_syn, r_norm)
+                    pge_grads, dX_pge = pge.backward(dA_raw)
+                    feat_grad = K.axpby(1.0, dX_pge, 1.0, dX)
             if self.trace:
                 self.trace("grads", step=(it, ol), loss=loss, feat_grad=feat_grad, pge_grads=pge_grads)
-            if self._pge_turn(it, ol):
-                if pge_grads is not None:
-                    self.optimizer_pge.step(pge_grads)
-            else:
-                self.optimizer_feat.step([feat_grad])
+            with K.timed("phase_optimizer"):
+                if self._pge_turn(it, ol):
+                    if pge_grads is not None:
+                        self.optimizer_pge.step(pge_grads)
+                else:
+                    self.optimizer_feat.step([feat_grad])
             if self.x_variant:
                 adj_inner = self.adj_syn
             else:
-                self.adj_syn_inner = pge.inference(self.feat_syn)
-                adj_inner, _ = K.dense_gcn_norm(self.adj_syn_inner)
-            for _ in range(inner_loop):
-                optimizer_model.step(model.train_grads(self.feat_syn, adj_inner))
+                with K.timed("phase_pge_inference"):
+                    self.adj_syn_inner = pge.inference(self.feat_syn, keep=True)
+                    adj_inner, r_inner = K.dense_gcn_norm(self.adj_syn_inner)
+                    self._pge_ready = (adj_inner, r_inner)
+            with K.timed("phase_inner_loop"):
+                for _ in range(inner_loop):
+                    optimizer_model.step(model.train_grads(self.feat_syn, adj_inner))
 
     def publish(self, data):
         n = self.nnodes_syn

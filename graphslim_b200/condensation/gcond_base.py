@@ -173,15 +173,22 @@ class GCondBase:
         With class sharding (model.lay.mask) only the owned classes are sampled in full and matched."""
         K = self.K
         pf = getattr(self, "_prefetch", None)
-        rb = pf.next() if pf is not None else self.sampler.sample(model.lay.mask)
+        t0 = time.perf_counter()
+        with K.timed("phase_sample_h2d"):
+            rb = pf.next() if pf is not None else self.sampler.sample(model.lay.mask)
+        self.host_wait_sampler_s = getattr(self, "host_wait_sampler_s", 0.0) + time.perf_counter() - t0
         if self.trace:
             self.trace("sample", rb=rb)
-        gr = model.real_grads(rb, self.features, self.ones_full)
-        model.syn_forward(self.feat_syn, self.adj_syn)
-        gs = model.syn_grads()
-        loss = K.zeros(1)
-        G = K.match(gs, gr, model.widths, model.is_bias, model.lay.coeff, self.args.dis_metric, loss)
-        dX, dA = model.syn_backward(G, need_dA=not model.identity_adj)
+        with K.timed("phase_real_grads"):
+            gr = model.real_grads(rb, self.features, self.ones_full)
+        with K.timed("phase_syn_forward_grads"):
+            model.syn_forward(self.feat_syn, self.adj_syn)
+            gs = model.syn_grads()
+        with K.timed("phase_match"):
+            loss = K.zeros(1)
+            G = K.match(gs, gr, model.widths, model.is_bias, model.lay.coeff, self.args.dis_metric, loss)
+        with K.timed("phase_syn_backward"):
+            dX, dA = model.syn_backward(G, need_dA=not model.identity_adj)
         return loss, dX, dA, rb
 
     def draw_model_weights(self, model):

@@ -215,6 +215,37 @@ __global__ void match_apply_kernel(int rows, int cols, const float* __restrict__
   G[(int64_t)r * ld + j] = alpha[j] * gr[(int64_t)r * ld + j] + beta[j] * gs_[(int64_t)r * ld + j];
 }
 
+// ---------------------------------------------------------------- per-class column sums (bias gradients)
+// out[out_block[g]*cols + c] = sum_{r in seg[g]..seg[g+1]} X[r, c]; blockIdx.y = group, a block owns 32 columns and
+// splits the segment's rows over its 8 warps.
+__global__ void segment_colsum_kernel(const int32_t* __restrict__ seg, const int32_t* __restrict__ out_block, int cols,
+                                      const float* __restrict__ X, int64_t ldx, float* __restrict__ out) {
+  __shared__ float sm[8][32];
+  const int g = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  const int r0 = seg[g], r1 = seg[g + 1];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < cols) {
+    int r = r0 + w;
+    for (; r + 24 < r1; r += 32) {
+      a0 += X[(int64_t)r * ldx + c];
+      a1 += X[(int64_t)(r + 8) * ldx + c];
+      a2 += X[(int64_t)(r + 16) * ldx + c];
+      a3 += X[(int64_t)(r + 24) * ldx + c];
+    }
+    for (; r < r1; r += 8) a0 += X[(int64_t)r * ldx + c];
+  }
+  sm[w][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (w == 0 && c < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += sm[i][threadIdx.x];
+    out[(int64_t)out_block[g] * cols + c] = v;
+  }
+}
+
 // ---------------------------------------------------------------- dense GCN normalisation
 // r_i = (1 + sum_j A_ij)^(-1/2);  Ahat_ij = (r_i * (A_ij + [i==j])) * r_j      (utils.py:429-439)
 __global__ void dense_norm_rowsum_kernel(int n, const float* __restrict__ A, float* __restrict__ r) {
@@ -373,6 +404,15 @@ int gs_match_apply_f32(int32_t rows, int32_t cols, const float* gs_, const float
   if (n == 0) return GS_OK;
   match_apply_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(rows, cols, gs_, gr, ld, alpha, beta, G);
   return finish_launch("match_apply");
+}
+
+int gs_segment_colsum_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t cols, const float* X,
+                          int64_t ldx, float* out, void* stream) {
+  GS_REQUIRE(G >= 0 && seg && out_block && cols >= 0 && X && out && ldx >= cols);
+  if (G == 0 || cols == 0) return GS_OK;
+  dim3 grid((cols + 31) / 32, G);
+  segment_colsum_kernel<<<grid, 256, 0, as_stream(stream)>>>(seg, out_block, cols, X, ldx, out);
+  return finish_launch("segment_colsum");
 }
 
 int gs_dense_gcn_norm_fwd_f32(int32_t n, const float* A, float* Ahat, float* r, void* stream) {

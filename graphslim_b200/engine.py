@@ -170,12 +170,11 @@ class SGC2(_ModelBase):
         for blk in reversed(rb.blocks_fwd):
             dU = K.spmm(blk.csr_t, dU)
         seg, ids, nb = rb.seg[-1], rb.out_block, self.lay.nblk
-        ones = _ones_col(K, Xg.shape[0])
         gW2 = K.gemm_grouped_tn(H1, dU, seg, ids, nb, aligned=rb.aligned)
-        gb2 = K.gemm_grouped_tn(ones, dU, seg, ids, nb, aligned=rb.aligned)
+        gb2 = K.segment_colsum(dU, seg, ids, nb)
         dA1 = K.relu_mask(K.gemm(dU, W2, tb=True), H1)
         gW1 = K.gemm_grouped_tn(Xg, dA1, seg, ids, nb, aligned=rb.aligned)
-        gb1 = K.gemm_grouped_tn(ones, dA1, seg, ids, nb, aligned=rb.aligned)
+        gb1 = K.segment_colsum(dA1, seg, ids, nb)
         return [gW1, gb1, gW2, gb2]
 
     def syn_forward(self, X, A):
@@ -277,13 +276,12 @@ class GCN2(_ModelBase):
         Z = K.bias_act(K.spmm(inner.csr, M2), b2, relu=False)
         _, R = K.softmax_residual(Z, rb.labels, rb.inv_b)
         ids, nb = rb.out_block, self.lay.nblk
-        gb2 = K.gemm_grouped_tn(_ones_col(K, R.shape[0]), R, rb.seg[0], ids, nb, aligned=rb.aligned)
+        gb2 = K.segment_colsum(R, rb.seg[0], ids, nb)
         dM2 = K.spmm(inner.csr_t, R)
         seg1 = rb.seg[1]
-        ones = _ones_col(K, T2.shape[0])
         gW2 = K.gemm_grouped_tn(H1, dM2, seg1, ids, nb, aligned=rb.aligned)
         dA1 = K.relu_mask(K.gemm(dM2, W2, tb=True), H1)
-        gb1 = K.gemm_grouped_tn(ones, dA1, seg1, ids, nb, aligned=rb.aligned)
+        gb1 = K.segment_colsum(dA1, seg1, ids, nb)
         gW1 = K.gemm_grouped_tn(T2, dA1, seg1, ids, nb, aligned=rb.aligned)
         return [gW1, gb1, gW2, gb2]
 

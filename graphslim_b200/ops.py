@@ -153,6 +153,16 @@ class CudaOps:
                    "gs_gemm_grouped_tn_f32")
         return out
 
+    def segment_colsum(self, X, seg, out_block, nblk):
+        """(1 x nblk*cols): block out_block[g] holds the column sums of rows seg[g]..seg[g+1] of X; other blocks zero."""
+        ldx = _mat(X, "X")
+        cols = X.shape[1]
+        G = seg.numel() - 1
+        out = self.zeros(1, nblk * cols) if G < nblk else self.empty(1, nblk * cols)
+        _lib.check(self.lib.gs_segment_colsum_f32(G, _ptr(seg), _ptr(out_block), cols, _ptr(X), ldx, _ptr(out),
+                                                  self.stream), "gs_segment_colsum_f32")
+        return out
+
     # -- sparse --------------------------------------------------------------------------------
     def spmm(self, csr, X, out=None, accumulate=False):
         ldx = _mat(X, "X")

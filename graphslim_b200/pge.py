@@ -66,9 +66,12 @@ class PGE:
             self._saved = (x, Pa, Pb, mean1, rstd1, H1, Y2, mean2, rstd2, A)
         return A
 
-    def inference(self, x):
-        """parametrized_adj.py:73-77: same forward without autograd (BN still in train mode)."""
-        return self.forward(x, keep=False)
+    def inference(self, x, keep=False):
+        """parametrized_adj.py:73-77: same forward without autograd (BN still in train mode).  `keep=True` retains the
+        activations: nothing changes PGE's parameters or feat_syn between this call and the next outer step's
+        `pge(feat_syn)` (gcond.py:63 -> :48; the inner loop only trains the condense model), so that forward would
+        recompute exactly these tensors and the caller may back-propagate through this pass instead."""
+        return self.forward(x, keep=keep)
 
     # ---------------------------------------------------------------------------------- backward
     def backward(self, dA):

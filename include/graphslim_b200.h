@@ -89,6 +89,11 @@ int gs_gemm_grouped_tn_f32(int32_t G, const int32_t* seg, const int32_t* out_blo
                            int32_t K_total, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                            int64_t ldc, int precision, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* out[out_block[g]*cols + c] = sum over rows seg[g]..seg[g+1] of X[r, c]  (per-class bias gradients); blocks of
+ * groups that are not listed are left untouched */
+int gs_segment_colsum_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t cols, const float* X,
+                          int64_t ldx, float* out, void* stream);
+
 /* ---- small fused kernels of the condense model ------------------------------------------- */
 /* Z[r,c] += bias[c]; optional ReLU (models/layers.py:48-51,378-381; models/sgc.py:41) */
 int gs_bias_act_f32(int32_t rows, int32_t cols, float* Z, int64_t ldz, const float* bias, int relu, void* stream);

@@ -53,6 +53,14 @@ class EmuOps:
             out[:, ob * N:(ob + 1) * N] = A[r0:r1].T @ B[r0:r1]
         return out
 
+    def segment_colsum(self, X, seg, out_block, nblk):
+        cols = X.shape[1]
+        out = torch.zeros(1, nblk * cols, device=self.device)
+        sl = seg.tolist()
+        for g, ob in enumerate(out_block.tolist()):
+            out[0, ob * cols:(ob + 1) * cols] = X[sl[g]:sl[g + 1]].sum(0)
+        return out
+
     # ---- sparse
     @staticmethod
     def _coo(csr):

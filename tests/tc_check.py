@@ -70,6 +70,23 @@ def run(mode):
     print(f"worst: 3xBF16 {worst[1]:.3e}, BF16 {worst[2]:.3e}")
     if mode == "bench":
         n, h = 909, 256
+        Y = torch.randn(n * n, h, device="cuda")
+        H = torch.randn(n * n, h, device="cuda")
+        Wm = torch.randn(h, h, device="cuda")
+        for name, fn in (("dW = dY^T H   (256x256, K=N'^2, TN)", lambda pr: K.gemm(Y, H, ta=True, precision=pr)),
+                         ("dX = dY W     (N'^2x256x256, NN)", lambda pr: K.gemm(Y, Wm, precision=pr))):
+            for prec in (1,):
+                fn(prec)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    fn(prec)
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / 5
+                print(f"{name} precision={prec}: {ms:.3f} ms, {2.0*n*n*h*h/ms/1e9:.1f} TFLOP/s", flush=True)
+        del Y, H
         A = torch.randn(n * n, h, device="cuda")
         W = torch.randn(h, h, device="cuda")
         out = torch.empty(n * n, h, device="cuda")

@@ -162,6 +162,15 @@ def test_gemm_grouped_tn(K, E):
     close(got, ref, rtol=2e-5)
 
 
+def test_segment_colsum(K, E):
+    gen = torch.Generator().manual_seed(41)
+    seg = torch.tensor([0, 64, 64, 700, 1000], dtype=torch.int32)
+    ob = torch.tensor([2, 0, 4, 1], dtype=torch.int32)
+    for cols in (1, 40, 256, 257):
+        X = torch.randn(1000, cols, generator=gen)
+        close(K.segment_colsum(X.cuda(), seg.cuda(), ob.cuda(), 5), E.segment_colsum(X, seg, ob, 5), rtol=1e-5)
+
+
 # ------------------------------------------------------------------------------------------ glue kernels
 def test_bias_relu_mask(K, E):
     gen = torch.Generator().manual_seed(5)

@@ -40,8 +40,10 @@ namespace tc {
 
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BK = 64;         // 64 bf16 = one 128-byte swizzle row
-constexpr int kProducerThreads = 128;
+constexpr int kProducerThreads = 256;                      // 8 warps: the A-operand conversion is latency bound
+constexpr int kProducerWarps = kProducerThreads / 32;
 constexpr int kEpilogueThreads = 128;
+constexpr int kMmaWarp = kProducerWarps + kEpilogueThreads / 32;
 constexpr int kThreads = kProducerThreads + kEpilogueThreads + 32;
 constexpr int kStages = 2;
 
@@ -203,20 +205,29 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// two floats -> packed bf16x2 hi word (element a in the low half) and packed lo word; one cvt.rn.bf16x2.f32 per word
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 // ------------------------------------------------------------------------------------------ producers
 // A (ROWS x 64) fp32 tile is fetched into registers first (all loads in flight at once: the producers are latency
 // bound otherwise) and converted / stored to shared memory later, so the fetch of k-block i+1 overlaps the wait for
 // a free stage and the conversion of k-block i.
 //
-// Thread -> element mapping, ROWS*16 float4 per tile, kProducerThreads threads, NLD = ROWS/8 float4 per thread:
+// Thread -> element mapping, ROWS*16 float4 per tile, kProducerThreads threads, NLD = ROWS*16/threads float4 each:
 //   K-contiguous source  (element (r,k) at P[r*ld + k]): float4 f = tid + 128*i covers row f>>4, k = 4*(f&15)..+3
 //   row-contiguous source (element (r,k) at P[k*ld + r]): warp w owns steps s = w + 4*i; a step covers 32 rows
 //       (8 lanes x float4) x 4 k-pairs; each lane packs (k, k+1) into one bf16x2 word per row and rotates its four row
 //       stores so the 32 lanes hit 32 distinct banks.
 template <int ROWS>
 struct TileRegs {
-  static constexpr int NLD = ROWS / 8;
+  static constexpr int NLD = ROWS * (BK / 4) / kProducerThreads;
+  static_assert(NLD >= 2 && NLD % 2 == 0, "tile too small for the producer thread count");
   float4 v[NLD];
 };
 
@@ -224,6 +235,14 @@ template <int ROWS>
 __device__ __forceinline__ void fetch_k_contig(TileRegs<ROWS>& t, const float* __restrict__ P, int64_t ld,
                                                int n_rows_total, int k_end, int r0, int k0, int tid) {
   const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(P) & 15) == 0);
+  if (vec_ok && r0 + ROWS <= n_rows_total && k0 + BK <= k_end) {
+    // interior tile: no guards, one base pointer, constant strides (rows advance by kProducerThreads/16 per step)
+    const float* src = P + (int64_t)(r0 + (tid >> 4)) * ld + k0 + (tid & 15) * 4;
+    const int64_t step = (int64_t)(kProducerThreads / 16) * ld;
+#pragma unroll
+    for (int i = 0; i < TileRegs<ROWS>::NLD; ++i) t.v[i] = __ldg(reinterpret_cast<const float4*>(src + i * step));
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < TileRegs<ROWS>::NLD; ++i) {
     const int f = tid + kProducerThreads * i;
@@ -252,22 +271,12 @@ __device__ __forceinline__ void store_k_contig(const TileRegs<ROWS>& t, uint8_t*
     const int f = tid + kProducerThreads * i;
     const int r = f >> 4, c4 = f & 15;
     const float4 v = t.v[i];
-    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-    split_bf16(v.x, h0, l0);
-    split_bf16(v.y, h1, l1);
-    split_bf16(v.z, h2, l2);
-    split_bf16(v.w, h3, l3);
+    uint2 ph, pl;
+    split_bf16x2(v.x, v.y, ph.x, pl.x);
+    split_bf16x2(v.z, v.w, ph.y, pl.y);
     const uint32_t off = sw128_offset(r, c4 * 4);
-    uint2 ph;
-    ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
     *reinterpret_cast<uint2*>(s_hi + off) = ph;
-    if (kWithLo) {
-      uint2 pl;
-      pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-      pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
-      *reinterpret_cast<uint2*>(s_lo + off) = pl;
-    }
+    if (kWithLo) *reinterpret_cast<uint2*>(s_lo + off) = pl;
   }
 }
 
@@ -323,15 +332,11 @@ __device__ __forceinline__ void store_r_contig(const TileRegs<ROWS>& t, uint8_t*
     for (int j = 0; j < 4; ++j) {
       const int jj = (j + (ri >> 1)) & 3;
       const int row = r4 + jj;
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(pick4(va, jj), h0, l0);
-      split_bf16(pick4(vb, jj), h1, l1);
+      uint32_t ph, pl;
+      split_bf16x2(pick4(va, jj), pick4(vb, jj), ph, pl);
       const uint32_t off = sw128_offset(row, kp * 2);
-      *reinterpret_cast<uint32_t*>(s_hi + off) =
-          (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      if (kWithLo)
-        *reinterpret_cast<uint32_t*>(s_lo + off) =
-            (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      *reinterpret_cast<uint32_t*>(s_hi + off) = ph;
+      if (kWithLo) *reinterpret_cast<uint32_t*>(s_lo + off) = pl;
     }
   }
 }
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* stage_out = reinterpret_cast<float*>(smem + kStages * kStageBytes);   // 4 warps x 32 x 33 floats
+  float* stage_out = reinterpret_cast<float*>(smem + kStages * kStageBytes);   // 4 warps x 32 x 36 floats
   __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_holder;
 
@@ -397,52 +402,57 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
     }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(&tmem_holder), kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_holder), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // ============================== producers ==============================
     const int tid = threadIdx.x;
     const int kblocks_total = (p.K + BK - 1) / BK;
-    // flattened (tile, k-block) work list with a one-item register prefetch
-    int tile = blockIdx.x;
-    int k0 = 0, k_end = 0, mb = 0, nb = 0;
-    Tile tl;
-    bool valid = seek_tile(p, tile, num_tiles, tl);
-    if (valid) {
-      mb = tl.mb;
-      nb = tl.nb;
-      k0 = tl.k_beg;
-      k_end = tl.k_end;
-    }
-    TileRegs<BM> nxt;
-    if (valid) {
-      if (p.ta) fetch_r_contig<BM>(nxt, p.A, p.lda, p.M, k_end, mb * BM, k0, tid);
-      else fetch_k_contig<BM>(nxt, p.A, p.lda, p.M, k_end, mb * BM, k0, tid);
-    }
+    // flattened (tile, k-block) work list; the fp32 A tiles of the next TWO items are kept in flight in registers
+    struct Cursor {
+      int tile, k0, k_end, mb, nb;
+      bool valid;
+    };
+    auto start = [&](Cursor& c, int first_tile) {
+      Tile tl;
+      c.tile = first_tile;
+      c.valid = seek_tile(p, c.tile, num_tiles, tl);
+      if (c.valid) {
+        c.mb = tl.mb;
+        c.nb = tl.nb;
+        c.k0 = tl.k_beg;
+        c.k_end = tl.k_end;
+      }
+    };
+    auto advance = [&](Cursor& c) {
+      c.k0 += BK;
+      if (c.k0 >= c.k_end) start(c, c.tile + gridDim.x);
+    };
+    auto fetch = [&](TileRegs<BM>& t, const Cursor& c) {
+      if (!c.valid) return;
+      if (p.ta) fetch_r_contig<BM>(t, p.A, p.lda, p.M, c.k_end, c.mb * BM, c.k0, tid);
+      else fetch_k_contig<BM>(t, p.A, p.lda, p.M, c.k_end, c.mb * BM, c.k0, tid);
+    };
+    Cursor cur, ahead;
+    start(cur, blockIdx.x);
+    TileRegs<BM> r0, r1;
+    fetch(r0, cur);
+    ahead = cur;
+    if (ahead.valid) advance(ahead);
+    fetch(r1, ahead);
     uint32_t it = 0;
-    while (valid) {
-      TileRegs<BM> cur = nxt;
-      const int c_k0 = k0, c_nb = nb;
-      // advance to the next work item and start its loads before touching shared memory
-      k0 += BK;
-      if (k0 >= k_end) {
-        tile += gridDim.x;
-        valid = seek_tile(p, tile, num_tiles, tl);
-        if (valid) {
-          mb = tl.mb;
-          nb = tl.nb;
-          k0 = tl.k_beg;
-          k_end = tl.k_end;
-        }
-      }
-      if (valid) {
-        if (p.ta) fetch_r_contig<BM>(nxt, p.A, p.lda, p.M, k_end, mb * BM, k0, tid);
-        else fetch_k_contig<BM>(nxt, p.A, p.lda, p.M, k_end, mb * BM, k0, tid);
-      }
+    while (cur.valid) {
+      const TileRegs<BM> now = r0;
+      const int c_k0 = cur.k0, c_nb = cur.nb;
+      // rotate: the item after next starts loading before this one is converted
+      r0 = r1;
+      cur = ahead;
+      if (ahead.valid) advance(ahead);
+      fetch(r1, ahead);
       const int s = it % kStages;
       const uint32_t ph = (it / kStages) & 1;
       mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
@@ -455,13 +465,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
         mbar_arrive_expect_tx(bar, kPlanes * kBBytes);
         bulk_g2s(smem_u32(sb_hi), src, kPlanes * kBBytes, bar);
       }
-      if (p.ta) store_r_contig<BM, kWithLo>(cur, sa_hi, sa_lo, tid);
-      else store_k_contig<BM, kWithLo>(cur, sa_hi, sa_lo, tid);
+      if (p.ta) store_r_contig<BM, kWithLo>(now, sa_hi, sa_lo, tid);
+      else store_k_contig<BM, kWithLo>(now, sa_hi, sa_lo, tid);
       fence_proxy_async();               // generic-proxy stores -> visible to the tensor-core (async) proxy
       mbar_arrive(smem_u32(&bar_full[s]));
       ++it;
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
     uint32_t it = 0, tcount = 0;
     Tile tl;
@@ -514,32 +524,59 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
       const uint32_t acc_ph = (tcount >> 1) & 1;
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_ph);
       tc_fence_after();
-      float* st = stage_out + q * (32 * 33);
+      float* st = stage_out + q * (32 * 36);            // 32 rows x 32 cols, row stride 36 floats (16 B aligned)
       const int row_base = mb * BM + q * 32;
+      const bool vec_c = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((tl.c_col & 3) == 0) &&
+                         (nb * BN + BN <= p.N) && (row_base + 32 <= p.M);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
         tmem_ld32(taddr, r);
         tmem_ld_wait();
-        // thread = row, r[j] = column j  ->  staging tile (padded, conflict free)  ->  lane = column
+        // thread = row, r[j] = column j  ->  staging tile  ->  8 lanes per row, float4 each: coalesced 128 B rows
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(st + lane * 36 + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                          __uint_as_float(r[j + 3]));
         __syncwarp();
-        const int gc = nb * BN + c0 + lane;
-        if (gc < p.N) {
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            const int row = row_base + rr;
-            if (row >= p.M) break;
-            float* c = p.C + (int64_t)row * p.ldc + tl.c_col + gc;
-            const float v = p.alpha * st[rr * 33 + lane];
+        const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+        if (vec_c) {
+          float* cbase = p.C + (int64_t)(row_base + rsub) * p.ldc + tl.c_col + nb * BN + c0 + c4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 v = *reinterpret_cast<const float4*>(st + (rsub + 4 * i) * 36 + c4);
+            float* c = cbase + (int64_t)(4 * i) * p.ldc;
+            v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
             if (use_atomics) {
-              atomicAdd(c, v);
-            } else if (p.beta == 0.f) {
-              *c = v;
+              atomicAdd(reinterpret_cast<float4*>(c), v);
             } else {
-              *c = fmaf(p.beta, *c, v);
+              if (p.beta != 0.f) {
+                const float4 o = *reinterpret_cast<const float4*>(c);
+                v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y);
+                v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
+              }
+              *reinterpret_cast<float4*>(c) = v;
+            }
+          }
+        } else {
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + rsub + 4 * i;
+            if (row >= p.M) break;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int gc = nb * BN + c0 + c4 + e;
+              if (gc >= p.N) break;
+              float* c = p.C + (int64_t)row * p.ldc + tl.c_col + gc;
+              const float v = p.alpha * st[(rsub + 4 * i) * 36 + c4 + e];
+              if (use_atomics) {
+                atomicAdd(c, v);
+              } else if (p.beta == 0.f) {
+                *c = v;
+              } else {
+                *c = fmaf(p.beta, *c, v);
+              }
             }
           }
         }
@@ -552,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -569,7 +606,7 @@ template <int BN, int NPASS>
 static int launch(Params& p, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
   constexpr int kPlanes = NPASS == 3 ? 2 : 1;
   constexpr bool kWithLo = NPASS == 3;
-  constexpr size_t smem = (size_t)kStages * kPlanes * (BM * BK * 2 + BN * BK * 2) + 4 * 32 * 33 * 4 + 1024;
+  constexpr size_t smem = (size_t)kStages * kPlanes * (BM * BK * 2 + BN * BK * 2) + 4 * 32 * 36 * 4 + 1024;
   {
     // B tile image into the caller's workspace
     const int kblocks_total = (p.K + BK - 1) / BK;

@@ -200,10 +200,10 @@ class SGC2(_ModelBase):
         dUc = self.dTz[0]                                         # (N, nc*C)
         ones = _ones_col(K, N)
         gW2 = K.gemm(self.H1, dUc, ta=True)
-        gb2 = K.gemm(ones, dUc, ta=True)
+        gb2 = K.colsum(dUc)
         self.dA1c = K.relu_mask(K.gemm(dUc.view(N * nc, C), self.W[2], tb=True), self.H1, groups=nc).view(N, nc * h)
         gW1 = K.gemm(self.X, self.dA1c, ta=True)
-        gb1 = K.gemm(ones, self.dA1c, ta=True)
+        gb1 = K.colsum(self.dA1c)
         return [gW1, gb1, gW2, gb2]
 
     def syn_backward(self, G, need_dA=True):
@@ -214,11 +214,11 @@ class SGC2(_ModelBase):
         ones = _ones_col(K, N)
         # tangent forward along G
         At = K.gemm(self.X, G1)
-        K.gemm(ones, g1, out=At, beta=1.0)
+        K.bias_act(At, g1.view(-1), relu=False)
         Ht = K.relu_mask(At, self.H1, groups=nc)
         Ut = K.gemm(Ht.view(N * nc, h), W2).view(N, nc * C)
         K.gemm(self.H1, G2, out=Ut, beta=1.0)
-        K.gemm(ones, g2, out=Ut, beta=1.0)
+        K.bias_act(Ut, g2.view(-1), relu=False)
         Tt = [Ut]
         for _ in range(self.k):
             Tt.append(self._prop(self.A, Tt[-1]))
@@ -252,10 +252,10 @@ class SGC2(_ModelBase):
             dU = self._prop(A, dU, transpose=True)
         ones = _ones_col(K, X.shape[0])
         gW2 = K.gemm(self.H1, dU, ta=True)
-        gb2 = K.gemm(ones, dU, ta=True).view(-1)
+        gb2 = K.colsum(dU).view(-1)
         dA1 = K.relu_mask(K.gemm(dU, W2, tb=True), self.H1)
         gW1 = K.gemm(X, dA1, ta=True)
-        gb1 = K.gemm(ones, dA1, ta=True).view(-1)
+        gb1 = K.colsum(dA1).view(-1)
         return [gW1, gb1, gW2, gb2]
 
 
@@ -301,12 +301,12 @@ class GCN2(_ModelBase):
         self.S, self.R = K.softmax_residual(self.Z, lay.labels, lay.inv_nc_row)
         self.Rexp = K.expand_class_blocks(self.R, lay.blk, nc)
         ones = _ones_col(K, N)
-        gb2 = K.gemm(ones, self.Rexp, ta=True)
+        gb2 = K.colsum(self.Rexp)
         self.dM2c = self._prop(self.A, self.Rexp, transpose=True)
         gW2 = K.gemm(self.H1, self.dM2c, ta=True)
         self.dA1c = K.relu_mask(K.gemm(self.dM2c.view(N * nc, C), self.W[2], tb=True), self.H1, groups=nc).view(
             N, nc * h)
-        gb1 = K.gemm(ones, self.dA1c, ta=True)
+        gb1 = K.colsum(self.dA1c)
         self.dM1c = self._prop(self.A, self.dA1c, transpose=True)
         gW1 = K.gemm(self.X, self.dM1c, ta=True)
         return [gW1, gb1, gW2, gb2]
@@ -319,12 +319,12 @@ class GCN2(_ModelBase):
         ones = _ones_col(K, N)
         M1t = K.gemm(self.X, G1)
         A1t = self._prop(self.A, M1t, fresh=True)
-        K.gemm(ones, g1, out=A1t, beta=1.0)
+        K.bias_act(A1t, g1.view(-1), relu=False)
         H1t = K.relu_mask(A1t, self.H1, groups=nc)
         M2t = K.gemm(H1t.view(N * nc, h), W2).view(N, nc * C)
         K.gemm(self.H1, G2, out=M2t, beta=1.0)
         Zt = self._prop(self.A, M2t, fresh=True)
-        K.gemm(ones, g2, out=Zt, beta=1.0)
+        K.bias_act(Zt, g2.view(-1), relu=False)
         q = K.pick_class_blocks(Zt, lay.blk, nc)
         dZ = K.softmax_jvp(self.S, q, lay.inv_nc_row)
         dA = None
@@ -350,11 +350,11 @@ class GCN2(_ModelBase):
         Z = self.syn_forward(X, A)
         _, R = K.softmax_residual(Z, lay.labels, lay.inv_n_row)
         ones = _ones_col(K, X.shape[0])
-        gb2 = K.gemm(ones, R, ta=True).view(-1)
+        gb2 = K.colsum(R).view(-1)
         dM2 = self._prop(A, R, transpose=True)
         gW2 = K.gemm(self.H1, dM2, ta=True)
         dA1 = K.relu_mask(K.gemm(dM2, W2, tb=True), self.H1)
-        gb1 = K.gemm(ones, dA1, ta=True).view(-1)
+        gb1 = K.colsum(dA1).view(-1)
         dM1 = self._prop(A, dA1, transpose=True)
         gW1 = K.gemm(X, dM1, ta=True)
         return [gW1, gb1, gW2, gb2]

@@ -163,6 +163,18 @@ class CudaOps:
                                                   self.stream), "gs_segment_colsum_f32")
         return out
 
+    def colsum(self, X):
+        """(1 x cols) column sums of X (bias gradients: 1^T X)."""
+        rows = X.shape[0]
+        cache = getattr(self, "_colsum_seg", None)
+        if cache is None:
+            cache = self._colsum_seg = {}
+        if rows not in cache:
+            cache[rows] = (torch.tensor([0, rows], dtype=torch.int32, device=self.device),
+                           torch.zeros(1, dtype=torch.int32, device=self.device))
+        seg, ob = cache[rows]
+        return self.segment_colsum(X, seg, ob, 1)
+
     # -- sparse --------------------------------------------------------------------------------
     def spmm(self, csr, X, out=None, accumulate=False):
         ldx = _mat(X, "X")

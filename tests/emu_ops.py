@@ -61,6 +61,9 @@ class EmuOps:
             out[0, ob * cols:(ob + 1) * cols] = X[sl[g]:sl[g + 1]].sum(0)
         return out
 
+    def colsum(self, X):
+        return X.sum(0, keepdim=True)
+
     # ---- sparse
     @staticmethod
     def _coo(csr):

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 # gemm_precision 0: every product in fp32 FMA -> the north-star fp32 bound (1e-4 on teacher-forced first steps).
 # gemm_precision 1 (default): large products on tcgen05 with the 3xBF16 split -> stated looser bound 1e-3; the
 # trajectory bounds are looser still because Adam amplifies rounding noise (see module docstring).
-TOL = {0: dict(first_tol=1e-4, traj_tol=3e-2), 1: dict(first_tol=1e-3, traj_tol=1e-1, later_tol=3e-2)}
+TOL = {0: dict(first_tol=1e-4, traj_tol=3e-2), 1: dict(first_tol=1e-3, traj_tol=1e-1, later_tol=3e-2, feat_tol=0.3)}
 
 
 @pytest.mark.parametrize("precision", [0, 1])

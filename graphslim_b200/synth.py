@@ -25,7 +25,8 @@ SHAPES = {
 def powerlaw_edges(n, und_edges, exponent=2.3, seed=0):
     """Return a (2, 2*und_edges) int64 edge_index of a simple undirected power-law graph.
 
-    Both directions are present, no self loops, no duplicates; sorted by (row, col).
+    Both directions are present, no self loops, no duplicates (edge order is unspecified: every consumer builds a
+    CSR from it).
     """
     rng = np.random.default_rng(seed)
     w = np.arange(1, n + 1, dtype=np.float64) ** (-1.0 / (exponent - 1.0))
@@ -50,10 +51,7 @@ def powerlaw_edges(n, und_edges, exponent=2.3, seed=0):
     if keys.size > need:
         keys = np.sort(rng.permutation(keys)[:need])
     lo, hi = keys // n, keys % n
-    row = np.concatenate([lo, hi])
-    col = np.concatenate([hi, lo])
-    order = np.argsort(row * n + col, kind="stable")
-    return np.stack([row[order], col[order]])
+    return np.stack([np.concatenate([lo, hi]), np.concatenate([hi, lo])])
 
 
 def make_graph(name=None, *, n=None, und_edges=None, d=None, c=None, split=None, per_class_train=None,

@@ -159,7 +159,7 @@ def run_reference(ns):
 def spmm_probe(agent, pk, iters=10):
     """Standalone full-graph A_hat @ X on the workload's graph (BASELINE config 5 at this shape)."""
     import torch
-    from graphslim_b200.graph_utils import build_row_chunks
+    from graphslim_b200.graph_utils import build_row_chunks, chunks_to_device
     from graphslim_b200.ops import Csr
     K = agent.K
     X = agent.features
@@ -167,7 +167,7 @@ def spmm_probe(agent, pk, iters=10):
     base = agent.adj_csr
     nnz = base.col.numel()
     # power-law rows (max degree 1e4-1e5) are split into <=512-nnz work items
-    chunks = tuple(torch.from_numpy(a).to(K.device) for a in build_row_chunks(base.rowptr.cpu().numpy(), 512))
+    chunks = chunks_to_device(build_row_chunks(base.rowptr.cpu().numpy(), 512), K.device)
     csr = Csr(base.rowptr, base.col, base.val, base.n_rows, base.n_cols, chunks)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=K.device)
     out = K.empty(n, F)

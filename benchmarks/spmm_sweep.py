@@ -22,7 +22,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from graphslim_b200.graph_utils import build_row_chunks  # noqa: E402
+from graphslim_b200.graph_utils import build_row_chunks, chunks_to_device  # noqa: E402
 from graphslim_b200.ops import Csr, CudaOps  # noqa: E402
 
 
@@ -89,7 +89,7 @@ def main():
         n = max(1000, nnz_t // avg)
         rowptr, col, val = powerlaw_csr(n, nnz_t, seed=nnz_t % 97 + avg, dev=dev)
         nnz = col.numel()
-        chunks = tuple(torch.from_numpy(a).to(dev) for a in build_row_chunks(rowptr.cpu().numpy(), 512))
+        chunks = chunks_to_device(build_row_chunks(rowptr.cpu().numpy(), 512), dev)
         csr = Csr(rowptr, col, val, n, n, chunks)
         max_deg = int((rowptr[1:] - rowptr[:-1]).max())
         tcsr = torch.sparse_csr_tensor(rowptr.long(), col.long(), val, size=(n, n))

@@ -55,24 +55,33 @@ struct V<1> {
   static __device__ __forceinline__ void atomic_add(float* p, T v) { atomicAdd(p, v); }
 };
 
+// Work items: [0, n_rows) = one row each (direct store); [n_rows, n_rows + n_chunks) = slices of the long rows
+// (degree > long_thr), accumulated with atomics into rows the caller has zeroed.  Row items skip long rows.
 struct Items {
   int32_t n_items;
+  int32_t n_rows;
+  int32_t long_thr;
   const int32_t* rowptr;
   const int32_t* chunk_row;
   const int32_t* chunk_beg;
   const int32_t* chunk_end;
 };
 
-__device__ __forceinline__ void item_range(const Items& it, int i, int& row, int& beg, int& end) {
-  if (it.chunk_row) {
-    row = it.chunk_row[i];
-    beg = it.chunk_beg[i];
-    end = it.chunk_end[i];
-  } else {
-    row = i;
-    beg = it.rowptr[i];
-    end = it.rowptr[i + 1];
+// returns false when the item has nothing to do; `atomic` tells the caller how to commit
+__device__ __forceinline__ bool item_range(const Items& it, int i, int& row, int& beg, int& end, bool& atomic) {
+  if (i >= it.n_rows) {
+    const int c = i - it.n_rows;
+    row = it.chunk_row[c];
+    beg = it.chunk_beg[c];
+    end = it.chunk_end[c];
+    atomic = true;
+    return true;
   }
+  row = i;
+  beg = it.rowptr[i];
+  end = it.rowptr[i + 1];
+  atomic = false;
+  return !(it.chunk_row && end - beg > it.long_thr);
 }
 
 // Wide rows: L = ceil(F/VEC) >= 32 vector columns, tiled by 32*NV per warp (blockIdx.y = column tile).
@@ -87,7 +96,9 @@ spmm_wide_kernel(Items it, const int32_t* __restrict__ col, const float* __restr
   const int item = blockIdx.x * kWarpsPerBlock + warp;
   if (item >= it.n_items) return;
   int row, beg, end;
-  item_range(it, item, row, beg, end);
+  bool atomic;
+  if (!item_range(it, item, row, beg, end, atomic)) return;
+  if (atomic) mode = 2;
   const int tile0 = blockIdx.y * (32 * NV);  // first vector column of this tile
   VT acc[NV];
 #pragma unroll
@@ -140,7 +151,9 @@ spmm_narrow_kernel(Items it, const int32_t* __restrict__ col, const float* __res
   const int item = blockIdx.x * kWarpsPerBlock + warp;
   if (item >= it.n_items) return;
   int row, beg, end;
-  item_range(it, item, row, beg, end);
+  bool atomic;
+  if (!item_range(it, item, row, beg, end, atomic)) return;
+  if (atomic) mode = 2;
   const int G = 32 / LPG;
   const int g = lane / LPG, l = lane % LPG;
   const bool live = l < L;
@@ -237,6 +250,19 @@ gather_rows_kernel(int n, const int32_t* __restrict__ idx, const float* __restri
   for (int l = lane; l < L; l += 32) V<VEC>::st(dst + (int64_t)l * VEC, V<VEC>::ld(src + (int64_t)l * VEC));
 }
 
+// zero the output rows of the long rows before their slices are accumulated
+template <int VEC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+zero_long_rows_kernel(int n_chunks, const int32_t* __restrict__ chunk_row, const int32_t* __restrict__ chunk_beg,
+                      const int32_t* __restrict__ rowptr, int L, float* __restrict__ Y, int64_t ldy) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kWarpsPerBlock + warp;
+  if (c >= n_chunks) return;
+  const int row = chunk_row[c];
+  if (chunk_beg[c] != rowptr[row]) return;        // only the first slice of a row clears it
+  for (int l = lane; l < L; l += 32) V<VEC>::st(Y + (int64_t)row * ldy + (int64_t)l * VEC, V<VEC>::zero());
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 csr_gcn_norm_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                     const float* __restrict__ a, const double* __restrict__ r, float* __restrict__ out) {
@@ -257,15 +283,23 @@ extern "C" {
 
 int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
                     int64_t ldx, int32_t F, float* Y, int64_t ldy, int accumulate, int32_t n_chunks,
-                    const int32_t* chunk_row, const int32_t* chunk_beg, const int32_t* chunk_end, void* stream) {
+                    int32_t long_thr, const int32_t* chunk_row, const int32_t* chunk_beg, const int32_t* chunk_end,
+                    void* stream) {
   if (n_rows == 0) return GS_OK;
   GS_REQUIRE(n_rows >= 0 && F > 0 && rowptr && X && Y && ldx >= F && ldy >= F);
-  GS_REQUIRE(n_chunks == 0 || (chunk_row && chunk_beg && chunk_end));
-  if (n_rows == 0) return GS_OK;
-  gs::Items it{n_chunks > 0 ? n_chunks : n_rows, rowptr, n_chunks > 0 ? chunk_row : nullptr, chunk_beg, chunk_end};
-  const int mode = n_chunks > 0 ? 2 : (accumulate ? 1 : 0);
+  GS_REQUIRE(n_chunks == 0 || (chunk_row && chunk_beg && chunk_end && long_thr > 0));
+  gs::Items it{n_rows + n_chunks, n_rows, long_thr, rowptr, n_chunks > 0 ? chunk_row : nullptr, chunk_beg, chunk_end};
+  const int mode = accumulate ? 1 : 0;
   cudaStream_t st = gs::as_stream(stream);
-  if (gs::vec4_ok(X, ldx, Y, ldy, F)) return gs::launch_spmm<4>(it, col, val, X, ldx, F, Y, ldy, mode, st);
+  const bool v4 = gs::vec4_ok(X, ldx, Y, ldy, F);
+  if (n_chunks > 0 && !accumulate) {
+    const int gx = (n_chunks + gs::kWarpsPerBlock - 1) / gs::kWarpsPerBlock;
+    if (v4) gs::zero_long_rows_kernel<4><<<gx, gs::kWarpsPerBlock * 32, 0, st>>>(n_chunks, chunk_row, chunk_beg, rowptr, F / 4, Y, ldy);
+    else gs::zero_long_rows_kernel<1><<<gx, gs::kWarpsPerBlock * 32, 0, st>>>(n_chunks, chunk_row, chunk_beg, rowptr, F, Y, ldy);
+    const int rc = gs::finish_launch("zero_long_rows");
+    if (rc) return rc;
+  }
+  if (v4) return gs::launch_spmm<4>(it, col, val, X, ldx, F, Y, ldy, mode, st);
   return gs::launch_spmm<1>(it, col, val, X, ldx, F, Y, ldy, mode, st);
 }
 

@@ -19,7 +19,8 @@ class Csr:
     def __init__(self, rowptr, col, val, n_rows, n_cols, chunks=None):
         self.rowptr, self.col, self.val = rowptr, col, val
         self.n_rows, self.n_cols = int(n_rows), int(n_cols)
-        self.chunks = chunks      # optional (chunk_row, chunk_beg, chunk_end) int32 tensors for long-row splitting
+        # optional long-row splitting: (chunk_row, chunk_beg, chunk_end, long_thr) from graph_utils.build_row_chunks
+        self.chunks = chunks
 
 
 def _ptr(t):
@@ -179,18 +180,16 @@ class CudaOps:
     def spmm(self, csr, X, out=None, accumulate=False):
         ldx = _mat(X, "X")
         F = X.shape[1]
-        n_chunks, cr, cb, ce = 0, None, None, None
+        n_chunks, thr, cr, cb, ce = 0, 0, None, None, None
         if csr.chunks is not None:
-            cr, cb, ce = csr.chunks
+            cr, cb, ce, thr = csr.chunks
             n_chunks = cr.numel()
         if out is None:
-            out = self.zeros(csr.n_rows, F) if n_chunks else self.empty(csr.n_rows, F)
-        elif n_chunks and not accumulate:
-            out.zero_()
+            out = self.empty(csr.n_rows, F)
         ldy = _mat(out, "out")
         _lib.check(self.lib.gs_spmm_csr_f32(csr.n_rows, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val), _ptr(X), ldx,
-                                            F, _ptr(out), ldy, int(accumulate), n_chunks, _ptr(cr), _ptr(cb),
-                                            _ptr(ce), self.stream), "gs_spmm_csr_f32")
+                                            F, _ptr(out), ldy, int(accumulate), n_chunks, int(thr), _ptr(cr),
+                                            _ptr(cb), _ptr(ce), self.stream), "gs_spmm_csr_f32")
         return out
 
     def spmm_scatter(self, csr, dY, out):

@@ -44,12 +44,12 @@ const char* gs_last_error(void);
  * condensation/gcond_base.py:214.  The backward w.r.t. the dense operand is the same call on
  * the transposed structure (A_hat is symmetric for the full graph; sampled blocks get their
  * transpose from gs_sample_step).
- * chunk_row/chunk_beg/chunk_end (may be NULL): optional split of long rows into work items of
- * bounded nnz (power-law tails); rows that are split must be listed consecutively and Y rows
- * are accumulated with atomics, so Y must be zeroed by the caller when n_chunks > 0.       */
+ * chunk_row/chunk_beg/chunk_end (may be NULL): slices (<= long_thr non-zeros each) of the rows whose
+ * degree exceeds long_thr (power-law tails).  Those rows are cleared and their slices accumulated with
+ * atomics; every other row is a plain warp-per-row item.  (graph_utils.build_row_chunks builds the list.) */
 int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val,
                     const float* X, int64_t ldx, int32_t F, float* Y, int64_t ldy, int accumulate,
-                    int32_t n_chunks, const int32_t* chunk_row, const int32_t* chunk_beg,
+                    int32_t n_chunks, int32_t long_thr, const int32_t* chunk_row, const int32_t* chunk_beg,
                     const int32_t* chunk_end, void* stream);
 
 /* Transpose-free backward through a rectangular block: dX[col[e],:] += val[e] * dY[r,:] (atomics).

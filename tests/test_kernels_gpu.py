@@ -77,13 +77,14 @@ def test_spmm_empty_rows_and_accumulate(K, E):
 
 
 def test_spmm_long_rows_chunked(K, E):
-    from graphslim_b200.graph_utils import build_row_chunks
+    from graphslim_b200.graph_utils import build_row_chunks, chunks_to_device
     gen = np.random.default_rng(5)
     csr = rand_csr(2000, 5000, 8, gen, powerlaw=True)
     X = torch.from_numpy(gen.standard_normal((5000, 128)).astype(np.float32))
     ref = E.spmm(csr, X)
     d = to_dev(csr, "cuda")
-    d.chunks = tuple(torch.from_numpy(a).cuda() for a in build_row_chunks(csr.rowptr.numpy(), 256))
+    d.chunks = chunks_to_device(build_row_chunks(csr.rowptr.numpy(), 64), "cuda")
+    assert d.chunks is not None
     got = K.spmm(d, X.cuda())
     close(got, ref)
 

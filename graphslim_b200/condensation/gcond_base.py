@@ -155,6 +155,7 @@ class GCondBase:
         fx = torch.zeros(n, ld, dtype=torch.float32, device=K.device)
         fx[:, :d] = torch.as_tensor(feats).float().to(K.device)
         self.features = fx[:, :d]
+        self.features_padded = fx          # zero pad columns: lets the feature-width SpMM use float4 for any d
         self.ones_full = torch.ones(n, 1, dtype=torch.float32, device=K.device)
         lab = np.asarray(labels).astype(np.int32)
         lt = np.asarray(data.labels_train)
@@ -180,7 +181,7 @@ class GCondBase:
         if self.trace:
             self.trace("sample", rb=rb)
         with K.timed("phase_real_grads"):
-            gr = model.real_grads(rb, self.features, self.ones_full)
+            gr = model.real_grads(rb, self.features, self.ones_full, self.features_padded)
         with K.timed("phase_syn_forward_grads"):
             model.syn_forward(self.feat_syn, self.adj_syn)
             gs = model.syn_grads()

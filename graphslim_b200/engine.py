@@ -81,14 +81,17 @@ class SGC1(_ModelBase):
     is_bias = [False, True]
 
     # ---- real side: H^r = A1 (A2 X[n_id]) does not depend on W, so propagate at feature width once
-    def real_grads(self, rb, X_full, ones_full):
+    def real_grads(self, rb, X_full, ones_full, X_padded=None):
         K = self.K
         W, b = self.W
-        T = K.spmm(rb.blocks_fwd[0].with_global_cols(), X_full)
+        d = X_full.shape[1]
+        Xp = X_full if X_padded is None else X_padded      # rows padded with zeros to a float4 multiple
+        T = K.spmm(rb.blocks_fwd[0].with_global_cols(), Xp)
         t = K.spmm(rb.blocks_fwd[0].with_global_cols(), ones_full)
         for blk in rb.blocks_fwd[1:]:
             T = K.spmm(blk.csr, T)
             t = K.spmm(blk.csr, t)
+        T = T[:, :d]
         Z = K.gemm(T, W)
         K.gemm(t, b.view(1, -1), out=Z, beta=1.0)
         _, R = K.softmax_residual(Z, rb.labels, rb.inv_b)
@@ -156,7 +159,7 @@ class SGC2(_ModelBase):
     widths = property(lambda s: [s.h, s.h, s.C, s.C])
     is_bias = [False, True, False, True]
 
-    def real_grads(self, rb, X_full, ones_full):
+    def real_grads(self, rb, X_full, ones_full, X_padded=None):
         K = self.K
         W1, b1, W2, b2 = self.W
         Xg = K.gather_rows(X_full, rb.nid)
@@ -266,11 +269,12 @@ class GCN2(_ModelBase):
     widths = property(lambda s: [s.h, s.h, s.C, s.C])
     is_bias = [False, True, False, True]
 
-    def real_grads(self, rb, X_full, ones_full):
+    def real_grads(self, rb, X_full, ones_full, X_padded=None):
         K = self.K
         W1, b1, W2, b2 = self.W
         outer, inner = rb.blocks_fwd
-        T2 = K.spmm(outer.with_global_cols(), X_full)               # (A2 X[n_id]) W1 == A2 (X[n_id] W1)
+        Xp = X_full if X_padded is None else X_padded
+        T2 = K.spmm(outer.with_global_cols(), Xp)[:, :X_full.shape[1]]   # (A2 X[n_id]) W1 == A2 (X[n_id] W1)
         H1 = K.bias_act(K.gemm(T2, W1), b1, relu=True)
         M2 = K.gemm(H1, W2)
         Z = K.bias_act(K.spmm(inner.csr, M2), b2, relu=False)

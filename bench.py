@@ -246,6 +246,8 @@ def run_ours(ns):
     t1.record()
     torch.cuda.synchronize()
     kernel_times = agent.K.stop_timing()
+    st = agent.sampler.stats
+    sampler_stats = {k: round(v / max(st["steps"], 1), 3) for k, v in st.items() if k != "steps"}
     launches = int(lib.gs_launch_count())
     host_wait_sampler = getattr(agent, "host_wait_sampler_s", 0.0)
     if world > 1:
@@ -325,6 +327,7 @@ def run_ours(ns):
         # and the host time the main thread spent waiting for the sampler worker
         "phases": {k[6:]: round(v[1] / ms, 4) for k, v in sorted(kernel_times.items()) if k.startswith("phase_")},
         "host_wait_sampler_frac": round(host_wait_sampler * 1e3 / ms, 4),
+        "sampler_ms_per_outer_step": sampler_stats,
     }
     print(json.dumps(line))
 

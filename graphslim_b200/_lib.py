@@ -62,6 +62,8 @@ SIGNATURES = {
     "gs_sampler_set_labels": (None, [c_vp, c_vp]),
     "gs_sampler_set_threads": (None, [c_vp, c_i32]),
     "gs_sampler_set_align": (None, [c_vp, c_i32]),
+    "gs_sampler_begin_step": (c_vp, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gs_sampler_finish_step": (c_i64, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gs_sampler_sample_step": (c_i64, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
 }
 

@@ -23,6 +23,7 @@
 //     dominated by ~2 DRAM misses per sampled edge.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <memory_resource>
@@ -79,6 +80,25 @@ struct HopOut {
   std::vector<int32_t> col;      // class-local column ids
   std::vector<int32_t> gcol;     // global ids (last hop only)
   std::vector<float> val;
+  // transpose of this class's block (sample-time CSC): rows = class-local columns, entries sorted by source row
+  std::vector<int32_t> t_rowptr, t_col;
+  std::vector<float> t_val;
+  void build_transpose(int32_t n_cols) {
+    const int32_t n_rows = (int32_t)rowptr.size() - 1;
+    const size_t nnz = col.size();
+    t_rowptr.assign((size_t)n_cols + 1, 0);
+    for (size_t e = 0; e < nnz; ++e) t_rowptr[(size_t)col[e] + 1]++;
+    for (int32_t j = 0; j < n_cols; ++j) t_rowptr[(size_t)j + 1] += t_rowptr[(size_t)j];
+    std::vector<int32_t> cursor(t_rowptr.begin(), t_rowptr.end() - 1);
+    t_col.resize(nnz);
+    t_val.resize(nnz);
+    for (int32_t r = 0; r < n_rows; ++r)
+      for (int32_t e = rowptr[(size_t)r]; e < rowptr[(size_t)r + 1]; ++e) {
+        const int32_t w = cursor[(size_t)col[(size_t)e]]++;
+        t_col[(size_t)w] = r;
+        t_val[(size_t)w] = val[(size_t)e];
+      }
+  }
 };
 
 struct ClassOut {
@@ -98,7 +118,8 @@ struct gs_sampler {
   int32_t nh;
   int32_t fan[8];
   const int32_t* labels = nullptr;
-  std::vector<std::vector<int32_t>> pos;    // per worker: node -> class-local index, -1 when unseen
+  std::vector<int32_t> pos_a;               // phase A (serial hops): node -> class-local index, -1 when unseen
+  std::vector<std::vector<int32_t>> pos;    // per phase-B worker
   int n_workers = 1;
   int32_t align = 1;                        // every class segment of every level is padded to a multiple of this
 };
@@ -217,7 +238,7 @@ gs_sampler* gs_sampler_create(int32_t n_nodes, const int64_t* rowptr, const int3
   unsigned hw = std::thread::hardware_concurrency();
   s->n_workers = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
   s->pos.assign((size_t)s->n_workers, std::vector<int32_t>());
-  s->pos[0].assign((size_t)n_nodes, -1);
+  s->pos_a.assign((size_t)n_nodes, -1);
   return s;
 }
 
@@ -240,23 +261,36 @@ void gs_sampler_set_threads(gs_sampler* s, int32_t n) {
 
 static inline int64_t align16(int64_t x) { return (x + 15) & ~int64_t(15); }
 
-int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* batch, const int64_t* batch_off,
-                               const uint8_t* materialise, uint32_t* mt_state, int32_t* mt_left, int32_t* mt_next,
-                               uint8_t* out, int64_t out_cap, int64_t* desc) {
-  if (!S || !batch || !batch_off || !mt_state || !out || !desc || n_class < 1) return GS_EINVAL;
+struct gs_sample_job {
+  int32_t n_class = 0;
+  std::vector<ClassOut> co;
+  std::vector<Mt19937> snap;          // generator state at the start of each class's last hop
+  std::vector<uint8_t> keepv;
+  int64_t us_a = 0;
+};
+
+// Phase A (serial, owns the generator): class batches -> all hops but the last, and the per-class segmentation of the
+// last hop's random stream.  Independent of phase B of earlier steps, so the two can run on different threads.
+gs_sample_job* gs_sampler_begin_step(gs_sampler* S, int32_t n_class, const int64_t* batch, const int64_t* batch_off,
+                                     const uint8_t* materialise, uint32_t* mt_state, int32_t* mt_left,
+                                     int32_t* mt_next) {
+  if (!S || !batch || !batch_off || !mt_state || n_class < 1) return nullptr;
+  const auto t_start = std::chrono::steady_clock::now();
   const int nh = S->nh;
   Mt19937 rng;
   std::memcpy(rng.s, mt_state, sizeof(rng.s));
   rng.left = *mt_left;
   rng.next = *mt_next;
-
-  std::vector<ClassOut> co((size_t)n_class);
-  std::vector<Mt19937> snap((size_t)n_class);  // generator state at the start of each class's last hop
-  std::vector<uint8_t> keepv((size_t)n_class);
-
-  // ---- phase A (serial): all hops but the last, and the stream segmentation of the last hop
+  gs_sample_job* J = new gs_sample_job();
+  J->n_class = n_class;
+  J->co.resize((size_t)n_class);
+  J->snap.resize((size_t)n_class);
+  J->keepv.resize((size_t)n_class);
+  std::vector<ClassOut>& co = J->co;
+  std::vector<Mt19937>& snap = J->snap;
+  std::vector<uint8_t>& keepv = J->keepv;
   {
-    std::vector<int32_t>& pos = S->pos[0];
+    std::vector<int32_t>& pos = S->pos_a;
     for (int32_t c = 0; c < n_class; ++c) {
       ClassOut& C = co[(size_t)c];
       const bool keep = materialise == nullptr || materialise[c] != 0;
@@ -266,7 +300,11 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
       C.nid.clear();
       for (int64_t t = batch_off[c]; t < batch_off[c + 1]; ++t) {
         const int32_t v = (int32_t)batch[t];
-        if (v < 0 || v >= S->n) return GS_EINVAL;
+        if (v < 0 || v >= S->n) {
+          for (int32_t u : C.nid) pos[(size_t)u] = -1;
+          delete J;
+          return nullptr;
+        }
         pos[(size_t)v] = (int32_t)C.nid.size();
         C.nid.push_back(v);
       }
@@ -283,7 +321,30 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
   std::memcpy(mt_state, rng.s, sizeof(rng.s));
   *mt_left = rng.left;
   *mt_next = rng.next;
+  J->us_a = (int64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();
+  return J;
+}
 
+// Phase B (parallel over classes) + packing.  Consumes and frees the job.
+int64_t gs_sampler_finish_step(gs_sampler* S, gs_sample_job* J, uint8_t* out, int64_t out_cap, int64_t* desc) {
+  if (!S || !J || !out || !desc) {
+    delete J;
+    return GS_EINVAL;
+  }
+  struct JobGuard {
+    gs_sample_job* j;
+    ~JobGuard() { delete j; }
+  } guard{J};
+  const int nh = S->nh;
+  const int32_t n_class = J->n_class;
+  std::vector<ClassOut>& co = J->co;
+  std::vector<Mt19937>& snap = J->snap;
+  std::vector<uint8_t>& keepv = J->keepv;
+  auto us_since = [&](std::chrono::steady_clock::time_point t0) {
+    return (int64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+  };
+  const int64_t us_a = J->us_a;
+  const auto t_b = std::chrono::steady_clock::now();
   // ---- phase B (parallel over classes): the last hop, each class on its own segment of the stream
   {
     std::atomic<int32_t> next_class{0};
@@ -300,6 +361,7 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
         sample_hop(S, pos, local, C.nid, S->fan[nh - 1], true, &C.hop[(size_t)nh - 1]);
         C.level_count[(size_t)nh] = (int32_t)C.nid.size();
         for (int32_t v : C.nid) pos[(size_t)v] = -1;
+        for (int h = 0; h < nh; ++h) C.hop[(size_t)h].build_transpose(C.level_count[(size_t)h + 1]);
       }
     };
     int n_keep = 0;
@@ -315,6 +377,8 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
     }
   }
 
+  const int64_t us_b = us_since(t_b);
+  const auto t_c = std::chrono::steady_clock::now();
   // ---- batch offsets
   std::vector<std::vector<int32_t>> seg((size_t)nh + 1, std::vector<int32_t>((size_t)n_class + 1, 0));
   // (padded to S->align rows per class: pad rows carry no edges, zero loss weight and node id 0, so they contribute
@@ -426,19 +490,40 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
       if (gcol && m) std::memcpy(gcol + e0, H.gcol.data(), m * 4);
       e0 += (int64_t)m;
     }
-    // transposed structure (sample-time CSC): deterministic, rows of A^T sorted by source row
-    std::memset(t_rowptr, 0, (size_t)(n_cols + 1) * 4);
-    for (int64_t e = 0; e < nnz; ++e) t_rowptr[col[e] + 1]++;
-    for (int32_t j = 0; j < n_cols; ++j) t_rowptr[j + 1] += t_rowptr[j];
-    cursor.assign(t_rowptr, t_rowptr + n_cols);
-    for (int32_t r = 0; r < n_rows; ++r)
-      for (int32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
-        const int32_t w = cursor[(size_t)col[e]]++;
-        t_col[w] = r;
-        t_val[w] = val[e];
+    // transposed structure: the batch is block diagonal, so it is the concatenation of the per-class transposes
+    // (built in parallel above) with row / entry offsets added
+    {
+      int64_t te = 0;
+      t_rowptr[0] = 0;
+      for (int32_t c = 0; c < n_class; ++c) {
+        const int32_t c0 = seg[(size_t)h + 1][(size_t)c], c1 = seg[(size_t)h + 1][(size_t)c + 1];
+        if (!keepv[(size_t)c]) continue;
+        const HopOut& H = co[(size_t)c].hop[(size_t)h];
+        const int32_t cols_c = (int32_t)H.t_rowptr.size() - 1;
+        const int32_t rbase = seg[(size_t)h][(size_t)c];
+        for (int32_t j = 0; j < cols_c; ++j) t_rowptr[c0 + j + 1] = (int32_t)(te + H.t_rowptr[(size_t)j + 1]);
+        const size_t m = H.t_col.size();
+        for (size_t i = 0; i < m; ++i) t_col[te + (int64_t)i] = H.t_col[i] + rbase;
+        if (m) std::memcpy(t_val + te, H.t_val.data(), m * 4);
+        te += (int64_t)m;
+        for (int32_t j = c0 + cols_c; j < c1; ++j) t_rowptr[j + 1] = (int32_t)te;      // pad columns: empty rows
       }
+    }
   }
+  desc[40] = us_a;                // serial hops + stream segmentation
+  desc[41] = us_b;                // parallel last hop
+  desc[42] = us_since(t_c);       // packing (offsets, transposes)
   return off;
+}
+
+
+int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* batch, const int64_t* batch_off,
+                               const uint8_t* materialise, uint32_t* mt_state, int32_t* mt_left, int32_t* mt_next,
+                               uint8_t* out, int64_t out_cap, int64_t* desc) {
+  if (!S || !batch || !batch_off || !mt_state || !out || !desc || n_class < 1) return GS_EINVAL;
+  gs_sample_job* J = gs_sampler_begin_step(S, n_class, batch, batch_off, materialise, mt_state, mt_left, mt_next);
+  if (!J) return GS_EINVAL;
+  return gs_sampler_finish_step(S, J, out, out_cap, desc);
 }
 
 }  // extern "C"

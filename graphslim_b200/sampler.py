@@ -9,6 +9,7 @@ reference's.  Output arrays are packed into one pinned buffer and moved to HBM w
 import ctypes
 import queue
 import threading
+import time
 
 import numpy as np
 import torch
@@ -106,6 +107,8 @@ class ClassSampler:
         self.desc = np.empty(64, dtype=np.int64)
         self.labels = None
         self.bytes_moved = 0              # host->device bytes of sampled blocks so far
+        self.stats = dict(steps=0, draw_batches_ms=0.0, serial_hops_ms=0.0, parallel_last_hop_ms=0.0, pack_ms=0.0,
+                          stage1_total_ms=0.0, stage2_total_ms=0.0)
         self._group_cache = {}
 
     def __del__(self):
@@ -129,25 +132,48 @@ class ClassSampler:
         off[1:] = np.cumsum([p.size for p in parts])
         return np.concatenate(parts), off
 
-    def sample_host(self, materialise=None):
-        """Runs the sampler; returns (bytes_used, desc copy).  The packed arrays are in self.pinned
-        (= self.ring[self.ring_pos]).  Safe to call from a worker thread: no CUDA work is issued here."""
+    def begin_host(self, materialise=None):
+        """Stage 1 (owns numpy's and torch's global generators): class batches + the serial hops.  Returns a job."""
+        t0 = time.perf_counter()
         batch, off = self.draw_batches()
-        self.ring_pos = (self.ring_pos + 1) % len(self.ring)
-        if self.ring_events[self.ring_pos] is not None:
-            self.ring_events[self.ring_pos].synchronize()
-        self.pinned = self.ring[self.ring_pos]
-        mat = None
-        if materialise is not None:
-            mat = np.ascontiguousarray(materialise, dtype=np.uint8)
+        t_draw = time.perf_counter() - t0
+        mat = None if materialise is None else np.ascontiguousarray(materialise, dtype=np.uint8)
         with _TorchMt() as g:
-            used = self.lib.gs_sampler_sample_step(self.handle, self.n_class, batch.ctypes.data, off.ctypes.data,
-                                                   mat.ctypes.data if mat is not None else None,
-                                                   g.state.ctypes.data, g.left.ctypes.data, g.next.ctypes.data,
-                                                   self.pinned.data_ptr(), self.cap, self.desc.ctypes.data)
+            job = self.lib.gs_sampler_begin_step(self.handle, self.n_class, batch.ctypes.data, off.ctypes.data,
+                                                 mat.ctypes.data if mat is not None else None, g.state.ctypes.data,
+                                                 g.left.ctypes.data, g.next.ctypes.data)
+        if not job:
+            raise _lib.GraphSlimLibraryError("gs_sampler_begin_step failed (class batch out of range?)")
+        st = self.stats
+        st["draw_batches_ms"] += t_draw * 1e3
+        st["stage1_total_ms"] += (time.perf_counter() - t0) * 1e3
+        return job
+
+    def finish_host(self, job):
+        """Stage 2: parallel last hop + packing into the next ring slot.  Returns (slot, bytes_used, desc copy).
+        No CUDA work is issued here; the slot is reused only after its previous H2D copy has completed."""
+        t0 = time.perf_counter()
+        self.ring_pos = (self.ring_pos + 1) % len(self.ring)
+        slot = self.ring_pos
+        if self.ring_events[slot] is not None:
+            self.ring_events[slot].synchronize()
+        self.pinned = self.ring[slot]
+        desc = np.empty(64, dtype=np.int64)
+        used = self.lib.gs_sampler_finish_step(self.handle, job, self.pinned.data_ptr(), self.cap, desc.ctypes.data)
         if used < 0:
-            raise _lib.GraphSlimLibraryError(f"gs_sampler_sample_step failed with code {used}")
-        return int(used), self.desc.copy()
+            raise _lib.GraphSlimLibraryError(f"gs_sampler_finish_step failed with code {used}")
+        st = self.stats
+        st["steps"] += 1
+        st["serial_hops_ms"] += desc[40] / 1e3
+        st["parallel_last_hop_ms"] += desc[41] / 1e3
+        st["pack_ms"] += desc[42] / 1e3
+        st["stage2_total_ms"] += (time.perf_counter() - t0) * 1e3
+        return slot, int(used), desc
+
+    def sample_host(self, materialise=None):
+        """Both stages back to back; returns (bytes_used, desc).  The packed arrays are in self.pinned."""
+        slot, used, desc = self.finish_host(self.begin_host(materialise))
+        return used, desc
 
     # ---- views --------------------------------------------------------------------------------
     @staticmethod
@@ -231,30 +257,56 @@ class ClassSampler:
 
 
 class _Prefetcher:
+    """Two worker threads: stage 1 (random streams, serial hops) feeds stage 2 (parallel last hop + packing); each is
+    at most one step ahead of its consumer.  The C++ calls release the GIL."""
+
     def __init__(self, sampler, n_steps, materialise):
         self.s, self.mat = sampler, materialise
+        self.q1 = queue.Queue(maxsize=1)
         self.q = queue.Queue(maxsize=1)
         self.stop = False
-        self.thread = threading.Thread(target=self._run, args=(n_steps,), daemon=True)
-        self.thread.start()
+        self.t1 = threading.Thread(target=self._stage1, args=(n_steps,), daemon=True)
+        self.t2 = threading.Thread(target=self._stage2, args=(n_steps,), daemon=True)
+        self.t1.start()
+        self.t2.start()
 
-    def _run(self, n_steps):
+    def _put(self, q, item):
+        while not self.stop:
+            try:
+                q.put(item, timeout=0.05)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def _get(self, q):
+        while not self.stop:
+            try:
+                return q.get(timeout=0.05)
+            except queue.Empty:
+                continue
+        return None
+
+    def _stage1(self, n_steps):
         try:
             for _ in range(n_steps):
                 if self.stop:
                     return
-                used, desc = self.s.sample_host(self.mat)
-                self._put((self.s.ring_pos, used, desc))
-        except BaseException as exc:           # surfaced by next()
-            self._put(exc)
+                self._put(self.q1, self.s.begin_host(self.mat))
+        except BaseException as exc:
+            self._put(self.q1, exc)
 
-    def _put(self, item):
-        while not self.stop:
-            try:
-                self.q.put(item, timeout=0.05)
-                return
-            except queue.Full:
-                continue
+    def _stage2(self, n_steps):
+        try:
+            for _ in range(n_steps):
+                job = self._get(self.q1)
+                if job is None:
+                    return
+                if isinstance(job, BaseException):
+                    raise job
+                self._put(self.q, self.s.finish_host(job))
+        except BaseException as exc:           # surfaced by next()
+            self._put(self.q, exc)
 
     def next(self):
         item = self.q.get()
@@ -264,9 +316,12 @@ class _Prefetcher:
         return self.s.upload(slot, used, desc, self.mat)
 
     def join(self):
-        """Normal end of an epoch: every step has been consumed.  After an error in the consumer the worker is told to
-        stop (the random streams are then left mid-epoch, as they would be after the same error in a serial loop)."""
-        self.stop = not self.q.empty() or self.stop
-        if self.thread.is_alive() and self.q.full():
-            self.stop = True
-        self.thread.join(timeout=60)
+        """Normal end of an epoch: every step has been consumed.  After an error in the consumer the workers are told
+        to stop (the random streams are then left mid-epoch, as they would be after the same error in a serial loop;
+        a job already begun is leaked rather than finished)."""
+        if self.t1.is_alive() or self.t2.is_alive():
+            if not (self.q.empty() and self.q1.empty()):
+                self.stop = True
+        self.t1.join(timeout=60)
+        self.t2.join(timeout=60)
+        self.stop = True

@@ -207,6 +207,15 @@ int64_t gs_sampler_sample_step(gs_sampler* s, int32_t n_class, const int64_t* ba
                                const uint8_t* materialise, uint32_t* mt_state, int32_t* mt_left, int32_t* mt_next,
                                uint8_t* out, int64_t out_cap, int64_t* desc);
 
+/* The same step in two calls so a caller can pipeline them on two threads: begin_step owns the random stream (all
+ * hops but the last + per-class segmentation of the last hop's stream, serial); finish_step samples the last hop of
+ * every class in parallel, packs, and frees the job.  finish_step(t) may overlap begin_step(t+1).                */
+typedef struct gs_sample_job gs_sample_job;
+gs_sample_job* gs_sampler_begin_step(gs_sampler* s, int32_t n_class, const int64_t* batch, const int64_t* batch_off,
+                                     const uint8_t* materialise, uint32_t* mt_state, int32_t* mt_left,
+                                     int32_t* mt_next);
+int64_t gs_sampler_finish_step(gs_sampler* s, gs_sample_job* job, uint8_t* out, int64_t out_cap, int64_t* desc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,9 @@ SIGNATURES = {
     "gs_dense_gcn_norm_fwd_f32": (c_int, [c_i32, c_vp, c_vp, c_vp, c_vp]),
     "gs_dense_gcn_norm_bwd_f32": (c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gs_pge_l1_stats_f32": (c_int, [c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "gs_pge_l1_stats_closed_f32": (c_int, [c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "gs_pge_bn1_bwd_closed_f32": (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                          c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gs_pge_l1_expand_f32": (c_int, [c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gs_col_stats_chunked_f32": (c_int, [c_i64, c_i32, c_vp, c_i32, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "gs_pge_l3_f32": (c_int, [c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -65,6 +68,14 @@ SIGNATURES = {
     "gs_sampler_begin_step": (c_vp, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gs_sampler_finish_step": (c_i64, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gs_sampler_sample_step": (c_i64, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gs_dsampler_create": (c_vp, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "gs_dsampler_destroy": (None, [c_vp]),
+    "gs_dsampler_out_capacity": (c_i64, [c_vp]),
+    "gs_dsampler_scratch_bytes": (c_i64, [c_vp]),
+    "gs_dsampler_set_rng": (c_int, [c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "gs_dsampler_get_rng": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gs_dsampler_sample_step": (c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp]),
+    "gs_uset_emul_order": (c_i64, [c_vp, c_i64, c_vp]),
 }
 
 _lib = None

@@ -15,7 +15,7 @@ import torch
 from .. import engine as _engine
 from ..ops import CudaOps, Csr
 from ..pge import PGE
-from ..sampler import ClassSampler
+from ..sampler import ClassSampler, DeviceClassSampler
 
 
 def _kernels(device, args):
@@ -163,8 +163,15 @@ class GCondBase:
         for c in range(data.nclass):
             members.append(np.asarray(data.idx_train)[lt == c] if args.setting == 'trans'
                            else np.arange(len(lt))[lt == c])
-        self.sampler = ClassSampler(*self.adj_host, members, args.dataset, args.nlayers, K.device)
-        self.sampler.set_labels(lab)
+        # neighbour sampling runs on the device against the resident CSR (bit-identical to the host sampler, which
+        # stays available as args.sampler = "host" and is what the CPU-emulated tests use)
+        kind = getattr(args, "sampler", "device")
+        if kind == "device" and K.device.type == "cuda":
+            self.sampler = DeviceClassSampler(self.adj_csr, members, args.dataset, args.nlayers, K.device,
+                                              labels=torch.from_numpy(lab))
+        else:
+            self.sampler = ClassSampler(*self.adj_host, members, args.dataset, args.nlayers, K.device)
+            self.sampler.set_labels(lab)
         if self.trace:
             self.trace("norm", rowptr=a_indptr, col=a_indices, val=val_host)
 

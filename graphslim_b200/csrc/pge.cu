@@ -418,6 +418,203 @@ pge_bn1_bwd_reduce_kernel(int n, int h, const float* __restrict__ dH1, const flo
   }
 }
 
+
+// ================================================================================================
+// Unchunked fast paths (every (i, j) pair in one BatchNorm batch: all configs but reddit at r >= 0.01)
+// ================================================================================================
+// Layer-1 pre-activations are Pa[j] + Pb[i] over the full product set {i} x {j}, so their batch statistics
+// factorise exactly:  mean = mean_j(Pa) + mean_i(Pb),  var = var_j(Pa) + var_i(Pb)  (the cross term sums to 0).
+// 2n rows are read instead of n^2.  col_mean[0][c] / [1][c] keep the column means of Pa / Pb for the backward.
+__global__ void __launch_bounds__(256)
+pge_l1_stats_closed_kernel(int n, int h, const float* __restrict__ Pa, const float* __restrict__ Pb, float eps,
+                           float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ col_mean) {
+  __shared__ double sm[2][8][33];
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;          // 32 columns x 8 row groups
+  const int c = blockIdx.x * 32 + cl;
+  const bool live = c < h;
+  double sa = 0.0, sb = 0.0;
+  if (live) {
+#pragma unroll 4
+    for (int r = rg; r < n; r += 8) {
+      sa += (double)__ldg(Pa + (int64_t)r * h + c);
+      sb += (double)__ldg(Pb + (int64_t)r * h + c);
+    }
+  }
+  sm[0][rg][cl] = sa;
+  sm[1][rg][cl] = sb;
+  __syncthreads();
+  double ma = 0.0, mb = 0.0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    ma += sm[0][g][cl];
+    mb += sm[1][g][cl];
+  }
+  ma /= (double)n;
+  mb /= (double)n;
+  __syncthreads();
+  double va = 0.0, vb = 0.0;
+  if (live) {
+#pragma unroll 4
+    for (int r = rg; r < n; r += 8) {
+      const double da = (double)__ldg(Pa + (int64_t)r * h + c) - ma, db = (double)__ldg(Pb + (int64_t)r * h + c) - mb;
+      va = fma(da, da, va);
+      vb = fma(db, db, vb);
+    }
+  }
+  sm[0][rg][cl] = va;
+  sm[1][rg][cl] = vb;
+  __syncthreads();
+  if (rg == 0 && live) {
+    double v = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) v += sm[0][g][cl] + sm[1][g][cl];
+    v /= (double)n;
+    mean[c] = (float)(ma + mb);
+    rstd[c] = (float)(1.0 / sqrt(v + (double)eps));
+    col_mean[c] = (float)ma;
+    col_mean[h + c] = (float)mb;
+  }
+}
+
+// E[r] = relu(bn2(Y2[r,:])) . w3 + b3 for h = 128*NQ: per-column constants live in registers, four rows per warp
+// iteration are in flight together (the generic kernel re-reads five constant vectors per row and is LSU bound).
+template <int NQ>
+__global__ void __launch_bounds__(256)
+pge_l3_fast_kernel(int64_t rows, const float* __restrict__ Y2, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ E) {
+  constexpr int h = 128 * NQ;
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float4 m[NQ], s[NQ], g[NQ], b[NQ], w[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int k = lane * 4 + 128 * q;
+    m[q] = ld4(mean + k); s[q] = ld4(rstd + k); g[q] = ld4(gamma + k); b[q] = ld4(beta + k); w[q] = ld4(w3 + k);
+  }
+  const float bias = b3[0];
+  for (int64_t r = warp * U; r < rows; r += nwarps * U) {
+    float4 y[U][NQ];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = (r + u < rows) ? r + u : rows - 1;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) y[u][q] = ld4(Y2 + rr * h + lane * 4 + 128 * q);
+    }
+    float acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float a = 0.f;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        a = fmaf(fmaxf(fmaf(g[q].x, (y[u][q].x - m[q].x) * s[q].x, b[q].x), 0.f), w[q].x, a);
+        a = fmaf(fmaxf(fmaf(g[q].y, (y[u][q].y - m[q].y) * s[q].y, b[q].y), 0.f), w[q].y, a);
+        a = fmaf(fmaxf(fmaf(g[q].z, (y[u][q].z - m[q].z) * s[q].z, b[q].z), 0.f), w[q].z, a);
+        a = fmaf(fmaxf(fmaf(g[q].w, (y[u][q].w - m[q].w) * s[q].w, b[q].w), 0.f), w[q].w, a);
+      }
+      acc[u] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    }
+    if (lane < U && r + lane < rows) {
+      const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+      E[r + lane] = v + bias;
+    }
+  }
+}
+
+// BN1 backward in ONE pass over dH1 (unchunked).  With g = dH1 * [relu mask] the gradients w.r.t. the factorised
+// layer-1 pre-activations only need linear reductions of g:
+//     Ga[j,:] = sum_i g[(i,j),:],  Gb[i,:] = sum_j g[(i,j),:],  t1 = sum g,  t2 = sum g * xhat,
+//     dPa[j,c] = gamma rstd (Ga[j,c] - n t1/m - (t2/m) rstd n (Pa[j,c] - mean_a[c]))      (m = n^2; dPb alike)
+// because sum_i xhat[(i,j),c] = rstd n (Pa[j,c] - mean_a[c]).  A CTA owns kB1I consecutive i and a range of j, so a
+// thread adds kB1I rows before it touches Ga (float4 atomics, L2 resident) and keeps its Gb partials in registers.
+constexpr int kB1I = 8;
+__global__ void __launch_bounds__(kRedThreads, 2)
+pge_bn1_bwd_pass_kernel(int n, int h, int jsplit, const float* __restrict__ dH1, const float* __restrict__ Pa,
+                        const float* __restrict__ Pb, const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ Ga,
+                        float* __restrict__ Gb, double* __restrict__ tsum) {
+  __shared__ __align__(16) float sm[2 * kRedThreads * 4];
+  const RedLayout L = red_layout(h);
+  const int i0 = blockIdx.x * kB1I;
+  const int ni = min(kB1I, n - i0);
+  const int per = (n + jsplit - 1) / jsplit;
+  const int j0 = blockIdx.y * per, j1 = min(n, j0 + per);
+  float4 acc[2] = {f4_zero(), f4_zero()};   // t1, t2
+  if (L.active) {
+    const int k = L.q * 4;
+    const float4 mu = ld4(mean + k), rs = ld4(rstd + k), g = ld4(gamma + k), b = ld4(beta + k);
+    float4 pb[kB1I], accB[kB1I];
+#pragma unroll
+    for (int ii = 0; ii < kB1I; ++ii) {
+      pb[ii] = ld4(Pb + (int64_t)min(i0 + ii, n - 1) * h + k);
+      accB[ii] = f4_zero();
+    }
+    for (int j = j0 + L.lane_row; j < j1; j += L.rl) {
+      const float4 pa = ld4(Pa + (int64_t)j * h + k);
+      float4 d[kB1I];
+#pragma unroll
+      for (int ii = 0; ii < kB1I; ++ii)
+        d[ii] = (ii < ni) ? ld4(dH1 + ((int64_t)(i0 + ii) * n + j) * h + k) : f4_zero();
+      float4 accA = f4_zero();
+#pragma unroll
+      for (int ii = 0; ii < kB1I; ++ii) {
+#define GS_B1P(cmp)                                                   \
+  {                                                                   \
+    const float xh = (pa.cmp + pb[ii].cmp - mu.cmp) * rs.cmp;         \
+    if (fmaf(g.cmp, xh, b.cmp) > 0.f) {                               \
+      accA.cmp += d[ii].cmp;                                          \
+      accB[ii].cmp += d[ii].cmp;                                      \
+      acc[0].cmp += d[ii].cmp;                                        \
+      acc[1].cmp = fmaf(d[ii].cmp, xh, acc[1].cmp);                   \
+    }                                                                 \
+  }
+        GS_B1P(x) GS_B1P(y) GS_B1P(z) GS_B1P(w)
+#undef GS_B1P
+      }
+      atomicAdd(reinterpret_cast<float4*>(Ga + (int64_t)j * h + k), accA);
+    }
+#pragma unroll
+    for (int ii = 0; ii < kB1I; ++ii)
+      if (ii < ni) atomicAdd(reinterpret_cast<float4*>(Gb + (int64_t)(i0 + ii) * h + k), accB[ii]);
+  }
+  double* const dst[2] = {tsum, tsum + h};
+  red_commit<2>(L, h, acc, sm, dst);
+}
+
+__global__ void pge_bn1_bwd_closed_final_kernel(int n, int h, const float* __restrict__ Pa, const float* __restrict__ Pb,
+                                                const float* __restrict__ col_mean, const float* __restrict__ rstd,
+                                                const float* __restrict__ gamma, const float* __restrict__ Ga,
+                                                const float* __restrict__ Gb, const double* __restrict__ tsum,
+                                                float* __restrict__ dPa, float* __restrict__ dPb,
+                                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nh = (int64_t)n * h;
+  if (idx < h) {
+    dbeta[idx] = (float)tsum[idx];
+    dgamma[idx] = (float)tsum[h + idx];
+  }
+  if (idx >= 2 * nh) return;
+  const bool second = idx >= nh;
+  const int64_t e = second ? idx - nh : idx;
+  const int c = (int)(e % h);
+  const double m = (double)n * (double)n;
+  const float a1n = (float)(tsum[c] * (double)n / m);            // sum over the reduced index of s1/m
+  const float a2 = (float)(tsum[h + c] / m);
+  const float rs = rstd[c];
+  const float p = second ? Pb[e] : Pa[e];
+  const float cm = col_mean[(second ? h : 0) + c];
+  const float G = second ? Gb[e] : Ga[e];
+  const float sx = rs * (float)n * (p - cm);
+  (second ? dPb : dPa)[e] = gamma[c] * rs * (G - a1n - sx * a2);
+}
+
 }  // namespace gs
 
 extern "C" {
@@ -437,6 +634,40 @@ int gs_pge_l1_stats_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, 
   if (rc) return rc;
   col_stats_final_kernel<0><<<(nchunk * h + 255) / 256, 256, 0, st>>>(n, h, Pa, Pb, nullptr, ch, work, eps, mean, rstd);
   return finish_launch("pge_l1_stats_final");
+}
+
+int gs_pge_l1_stats_closed_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, float eps, float* mean,
+                               float* rstd, float* col_mean, void* stream) {
+  GS_REQUIRE(n > 0 && h > 0 && Pa && Pb && mean && rstd && col_mean);
+  pge_l1_stats_closed_kernel<<<(h + 31) / 32, 256, 0, as_stream(stream)>>>(n, h, Pa, Pb, eps, mean, rstd, col_mean);
+  return finish_launch("pge_l1_stats_closed");
+}
+
+int gs_pge_bn1_bwd_closed_f32(int32_t n, int32_t h, const float* dH1, const float* Pa, const float* Pb,
+                              const float* mean, const float* rstd, const float* gamma, const float* beta,
+                              const float* col_mean, float* dPa, float* dPb, float* dgamma, float* dbeta, void* work,
+                              int64_t work_bytes, void* stream) {
+  GS_REQUIRE(n > 0 && h > 0 && h % 4 == 0 && h <= 1024 && dH1 && Pa && Pb && mean && rstd && gamma && beta &&
+             col_mean && dPa && dPb && dgamma && dbeta && work);
+  const int64_t need = (int64_t)sizeof(double) * 2 * h + (int64_t)sizeof(float) * 2 * n * h;
+  GS_REQUIRE(work_bytes >= need && (reinterpret_cast<uintptr_t>(work) & 15) == 0);
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(work, 0, (size_t)need, st);
+  double* tsum = reinterpret_cast<double*>(work);
+  float* Ga = reinterpret_cast<float*>(tsum + 2 * h);
+  float* Gb = Ga + (int64_t)n * h;
+  const int gx = (n + kB1I - 1) / kB1I;
+  int jsplit = (4 * kNumSMs + gx - 1) / gx;
+  if (jsplit < 1) jsplit = 1;
+  if (jsplit > n) jsplit = n;
+  pge_bn1_bwd_pass_kernel<<<dim3(gx, jsplit), kRedThreads, 0, st>>>(n, h, jsplit, dH1, Pa, Pb, mean, rstd, gamma, beta,
+                                                                   Ga, Gb, tsum);
+  int rc = finish_launch("pge_bn1_bwd_pass");
+  if (rc) return rc;
+  const int64_t cnt = 2 * (int64_t)n * h;
+  pge_bn1_bwd_closed_final_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(n, h, Pa, Pb, col_mean, rstd, gamma, Ga,
+                                                                              Gb, tsum, dPa, dPb, dgamma, dbeta);
+  return finish_launch("pge_bn1_bwd_closed_final");
 }
 
 int gs_pge_l1_expand_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, int32_t nchunk,
@@ -472,6 +703,13 @@ int gs_pge_l3_f32(int64_t rows, int32_t h, const float* Y2, int32_t nchunk, cons
   GS_PGE_COMMON_REQ;
   GS_REQUIRE(rows > 0 && Y2 && mean && rstd && gamma && beta && w3 && b3 && E);
   Chunks ch{nchunk, chunk_off};
+  if (nchunk == 1 && (h == 128 || h == 256) && (reinterpret_cast<uintptr_t>(Y2) & 15) == 0) {
+    const int64_t want4 = (rows + 31) / 32;
+    const unsigned g4 = (unsigned)(want4 < kNumSMs * 8 ? want4 : kNumSMs * 8);
+    if (h == 128) pge_l3_fast_kernel<1><<<g4, 256, 0, as_stream(stream)>>>(rows, Y2, mean, rstd, gamma, beta, w3, b3, E);
+    else pge_l3_fast_kernel<2><<<g4, 256, 0, as_stream(stream)>>>(rows, Y2, mean, rstd, gamma, beta, w3, b3, E);
+    return finish_launch("pge_l3_fast");
+  }
   const int64_t want = (rows + 7) / 8;
   const unsigned grid = (unsigned)(want < 148 * 32 ? want : 148 * 32);
   pge_l3_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, h, Y2, ch, mean, rstd, gamma, beta, w3, b3, E);

@@ -330,6 +330,26 @@ class CudaOps:
                    "gs_pge_l1_stats_f32")
         return mean, rstd
 
+    def pge_l1_stats_closed(self, Pa, Pb, eps=1e-5):
+        """Unchunked BN1 statistics from the column statistics of Pa and Pb; returns (mean 1xh, rstd 1xh, col_mean 2xh)."""
+        n, h = Pa.shape
+        mean, rstd, cm = self.empty(1, h), self.empty(1, h), self.empty(2, h)
+        _lib.check(self.lib.gs_pge_l1_stats_closed_f32(n, h, _ptr(Pa), _ptr(Pb), eps, _ptr(mean), _ptr(rstd), _ptr(cm),
+                                                       self.stream), "gs_pge_l1_stats_closed_f32")
+        return mean, rstd, cm
+
+    def pge_bn1_bwd_closed(self, dH1, Pa, Pb, mean, rstd, gamma, beta, col_mean):
+        """Unchunked BN1+ReLU backward in one pass over dH1; returns (dPa, dPb, dgamma1, dbeta1)."""
+        n, h = Pa.shape
+        dPa, dPb, dg, db = self.empty(n, h), self.empty(n, h), self.empty(h), self.empty(h)
+        nbytes = 16 * h + 8 * n * h
+        work = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gs_pge_bn1_bwd_closed_f32(n, h, _ptr(dH1), _ptr(Pa), _ptr(Pb), _ptr(mean), _ptr(rstd),
+                                                      _ptr(gamma), _ptr(beta), _ptr(col_mean), _ptr(dPa), _ptr(dPb),
+                                                      _ptr(dg), _ptr(db), _ptr(work), work.numel() * 8, self.stream),
+                   "gs_pge_bn1_bwd_closed_f32")
+        return dPa, dPb, dg, db
+
     def pge_l1_expand(self, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
         n, h = Pa.shape
         H1 = self.empty(n * n, h)

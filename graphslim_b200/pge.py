@@ -55,7 +55,11 @@ class PGE:
         W1 = self.W[0]
         Pa = K.gemm(x, W1[:, :d], tb=True)                       # layer 1, first half: indexed by j
         Pb = K.gemm(x, W1[:, d:], tb=True)                       # second half: indexed by i (bias cancels in BN)
-        mean1, rstd1 = K.pge_l1_stats(Pa, Pb, self.chunk_off, self.eps)
+        cm1 = None
+        if self.nchunks == 1:                                     # product-set statistics factorise: 2n rows, not n^2
+            mean1, rstd1, cm1 = K.pge_l1_stats_closed(Pa, Pb, self.eps)
+        else:
+            mean1, rstd1 = K.pge_l1_stats(Pa, Pb, self.chunk_off, self.eps)
         H1 = K.pge_l1_expand(Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0])
         with K.timed("pge_l2_fwd"):
             Y2 = K.gemm(H1, self.W[1], tb=True)                  # the N'^2 x h x h product (bias cancels in BN)
@@ -63,7 +67,7 @@ class PGE:
         E = K.pge_l3(Y2, self.chunk_off, mean2, rstd2, self.gamma[1], self.beta[1], self.W[2].view(-1), self.b[2])
         A = K.pge_symm_sigmoid(E, n)
         if keep:
-            self._saved = (x, Pa, Pb, mean1, rstd1, H1, Y2, mean2, rstd2, A)
+            self._saved = (x, Pa, Pb, mean1, rstd1, cm1, H1, Y2, mean2, rstd2, A)
         return A
 
     def inference(self, x, keep=False):
@@ -77,7 +81,7 @@ class PGE:
     def backward(self, dA):
         """Returns (grads in parameters() order, dX)."""
         K, n, d, h = self.K, self.n, self.d, self.h
-        x, Pa, Pb, mean1, rstd1, H1, Y2, mean2, rstd2, A = self._saved
+        x, Pa, Pb, mean1, rstd1, cm1, H1, Y2, mean2, rstd2, A = self._saved
         W1, W2, w3 = self.W[0], self.W[1], self.W[2].view(-1)
         dE = K.pge_symm_sigmoid_bwd(dA, A)
         s1, s2, dw3, db3 = K.pge_l3_bwd_stats(Y2, dE, self.chunk_off, mean2, rstd2, self.gamma[1], self.beta[1], w3)
@@ -87,10 +91,14 @@ class PGE:
             dW2 = K.gemm(dY2, H1, ta=True)                        # (h_out, h_in), K = N'^2
         with K.timed("pge_l2_bwd_dx"):
             dH1 = K.gemm(dY2, W2)                                 # N'^2 x h
-        t1, t2 = K.pge_bn1_bwd_stats(dH1, Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0])
-        dgamma1, dbeta1 = t2.sum(0), t1.sum(0)
-        dPa, dPb = K.pge_bn1_bwd_reduce(dH1, Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0],
-                                        t1, t2)
+        if cm1 is not None:                                       # one pass over dH1 (linear reductions only)
+            dPa, dPb, dgamma1, dbeta1 = K.pge_bn1_bwd_closed(dH1, Pa, Pb, mean1, rstd1, self.gamma[0], self.beta[0],
+                                                             cm1)
+        else:
+            t1, t2 = K.pge_bn1_bwd_stats(dH1, Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0])
+            dgamma1, dbeta1 = t2.sum(0), t1.sum(0)
+            dPa, dPb = K.pge_bn1_bwd_reduce(dH1, Pa, Pb, self.chunk_off, mean1, rstd1, self.gamma[0], self.beta[0],
+                                            t1, t2)
         dW1 = K.empty(h, 2 * d)
         K.gemm(dPa, x, ta=True, out=dW1[:, :d])
         K.gemm(dPb, x, ta=True, out=dW1[:, d:])

@@ -65,7 +65,62 @@ class RealBatch:
     pass
 
 
-class ClassSampler:
+class _Unpack:
+    """Tensor views over the packed bytes of one step (needs self.nh, self.n_class, self.align, self._group_cache)."""
+
+    @staticmethod
+    def _view(buf, off, count, dtype):
+        nbytes = count * 4
+        return buf[off:off + nbytes].view(dtype)
+
+    def unpack(self, buf, desc, materialise=None):
+        """Build a RealBatch of tensor views over `buf` (host or device copy of the packed bytes)."""
+        nh, nc = self.nh, self.n_class
+        rb = RealBatch()
+        counts = [int(desc[2 + l]) for l in range(nh + 1)]
+        segs = self._view(buf, int(desc[8]), (nh + 1) * (nc + 1), torch.int32).view(nh + 1, nc + 1)
+        rb.counts = counts
+        rb.nid = self._view(buf, int(desc[9]), counts[nh], torch.int32)
+        rb.tcls = self._view(buf, int(desc[10]), counts[0], torch.int32)
+        rb.inv_b = self._view(buf, int(desc[11]), counts[0], torch.float32)
+        rb.target_ids = self._view(buf, int(desc[12]), counts[0], torch.int32)
+        rb.labels = self._view(buf, int(desc[13]), counts[0], torch.int32) if desc[13] >= 0 else None
+        rb.aligned = self.align % 64 == 0      # class segments start on tensor-core tile boundaries
+        rb.cnt = self._view(buf, int(desc[14]), (nh + 1) * nc, torch.int32).view(nh + 1, nc)   # unpadded class sizes
+        blocks = []
+        for h in range(nh):
+            d = desc[16 + 8 * h: 24 + 8 * h]
+            nnz = int(d[0])
+            rows, cols = counts[h], counts[h + 1]
+            csr = Csr(self._view(buf, int(d[1]), rows + 1, torch.int32), self._view(buf, int(d[2]), nnz, torch.int32),
+                      self._view(buf, int(d[3]), nnz, torch.float32), rows, cols)
+            csr_t = Csr(self._view(buf, int(d[4]), cols + 1, torch.int32),
+                        self._view(buf, int(d[5]), nnz, torch.int32),
+                        self._view(buf, int(d[6]), nnz, torch.float32), cols, rows)
+            gcol = self._view(buf, int(d[7]), nnz, torch.int32) if d[7] >= 0 else None
+            blocks.append(Block(csr, csr_t, gcol))
+        rb.blocks = blocks
+        rb.blocks_fwd = blocks[::-1]          # application order: outermost hop first (adjs[::-1] in PyG)
+        # groups = materialised classes; per-level row segments restricted to them
+        key = (None if materialise is None else tuple(int(m) for m in materialise), str(buf.device))
+        cached = self._group_cache.get(key)
+        if cached is None:          # constant across steps: build once (a fresh torch.tensor(...) would sync the stream)
+            keep = np.arange(nc) if materialise is None else np.nonzero(np.asarray(materialise))[0]
+            cached = (torch.tensor(keep, dtype=torch.int32, device=buf.device),
+                      torch.arange(len(keep), dtype=torch.int32, device=buf.device),
+                      torch.tensor(np.concatenate([keep, [nc]]), dtype=torch.int64, device=buf.device),
+                      len(keep) == nc)
+            self._group_cache[key] = cached
+        rb.class_ids, rb.out_block, idx, all_classes = cached      # out_block: class-column block per group
+        if all_classes:
+            rb.seg = [segs[l] for l in range(nh + 1)]
+        else:
+            # segments of skipped classes are empty, so dropping them keeps the offsets contiguous
+            rb.seg = [segs[l][idx].contiguous() for l in range(nh + 1)]
+        return rb
+
+
+class ClassSampler(_Unpack):
     def __init__(self, adj_rowptr, adj_col, adj_val, members, dataset, nlayers, device, batch=256, align=64):
         """adj_*: CSR of the normalised graph on the host (int64 rowptr, int32 col, fp32 val);
         members[c]: node ids of class c (global ids in 'trans', train-local in 'ind')."""
@@ -175,58 +230,6 @@ class ClassSampler:
         slot, used, desc = self.finish_host(self.begin_host(materialise))
         return used, desc
 
-    # ---- views --------------------------------------------------------------------------------
-    @staticmethod
-    def _view(buf, off, count, dtype):
-        nbytes = count * 4
-        return buf[off:off + nbytes].view(dtype)
-
-    def unpack(self, buf, desc, materialise=None):
-        """Build a RealBatch of tensor views over `buf` (host or device copy of the packed bytes)."""
-        nh, nc = self.nh, self.n_class
-        rb = RealBatch()
-        counts = [int(desc[2 + l]) for l in range(nh + 1)]
-        segs = self._view(buf, int(desc[8]), (nh + 1) * (nc + 1), torch.int32).view(nh + 1, nc + 1)
-        rb.counts = counts
-        rb.nid = self._view(buf, int(desc[9]), counts[nh], torch.int32)
-        rb.tcls = self._view(buf, int(desc[10]), counts[0], torch.int32)
-        rb.inv_b = self._view(buf, int(desc[11]), counts[0], torch.float32)
-        rb.target_ids = self._view(buf, int(desc[12]), counts[0], torch.int32)
-        rb.labels = self._view(buf, int(desc[13]), counts[0], torch.int32) if desc[13] >= 0 else None
-        rb.aligned = self.align % 64 == 0      # class segments start on tensor-core tile boundaries
-        rb.cnt = self._view(buf, int(desc[14]), (nh + 1) * nc, torch.int32).view(nh + 1, nc)   # unpadded class sizes
-        blocks = []
-        for h in range(nh):
-            d = desc[16 + 8 * h: 24 + 8 * h]
-            nnz = int(d[0])
-            rows, cols = counts[h], counts[h + 1]
-            csr = Csr(self._view(buf, int(d[1]), rows + 1, torch.int32), self._view(buf, int(d[2]), nnz, torch.int32),
-                      self._view(buf, int(d[3]), nnz, torch.float32), rows, cols)
-            csr_t = Csr(self._view(buf, int(d[4]), cols + 1, torch.int32),
-                        self._view(buf, int(d[5]), nnz, torch.int32),
-                        self._view(buf, int(d[6]), nnz, torch.float32), cols, rows)
-            gcol = self._view(buf, int(d[7]), nnz, torch.int32) if d[7] >= 0 else None
-            blocks.append(Block(csr, csr_t, gcol))
-        rb.blocks = blocks
-        rb.blocks_fwd = blocks[::-1]          # application order: outermost hop first (adjs[::-1] in PyG)
-        # groups = materialised classes; per-level row segments restricted to them
-        key = (None if materialise is None else tuple(int(m) for m in materialise), str(buf.device))
-        cached = self._group_cache.get(key)
-        if cached is None:          # constant across steps: build once (a fresh torch.tensor(...) would sync the stream)
-            keep = np.arange(nc) if materialise is None else np.nonzero(np.asarray(materialise))[0]
-            cached = (torch.tensor(keep, dtype=torch.int32, device=buf.device),
-                      torch.arange(len(keep), dtype=torch.int32, device=buf.device),
-                      torch.tensor(np.concatenate([keep, [nc]]), dtype=torch.int64, device=buf.device),
-                      len(keep) == nc)
-            self._group_cache[key] = cached
-        rb.class_ids, rb.out_block, idx, all_classes = cached      # out_block: class-column block per group
-        if all_classes:
-            rb.seg = [segs[l] for l in range(nh + 1)]
-        else:
-            # segments of skipped classes are empty, so dropping them keeps the offsets contiguous
-            rb.seg = [segs[l][idx].contiguous() for l in range(nh + 1)]
-        return rb
-
     def upload(self, slot, used, desc, materialise=None):
         """One H2D copy of the packed bytes of ring slot `slot`, then device views."""
         src = self.ring[slot]
@@ -325,3 +328,225 @@ class _Prefetcher:
         self.t1.join(timeout=60)
         self.t2.join(timeout=60)
         self.stop = True
+
+
+# =================================================================================================================
+# Device-side sampler (csrc/device_sampler.cu): same blocks, same random streams, no host sampling / H2D of blocks
+# =================================================================================================================
+class DeviceClassSampler(_Unpack):
+    """Drop-in for ClassSampler on a CUDA device.  numpy's generator still draws the class batches on the host (a
+    sequential Fisher-Yates per class, loader.py:222); torch's CPU generator state is checked out to the device at the
+    start of an epoch, advanced there by the sampling kernels, and written back when the epoch ends, so both streams
+    are consumed exactly as the reference consumes them."""
+
+    RING = 3
+
+    def __init__(self, adj_csr, members, dataset, nlayers, device, labels=None, batch=256, align=64):
+        """adj_csr: ops.Csr of the normalised graph in HBM (int32 rowptr/col, fp32 val); labels: int32 device tensor."""
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.GraphSlimLibraryError("DeviceClassSampler needs a CUDA device")
+        self.adj = adj_csr
+        self.n = int(adj_csr.n_rows)
+        self.members = [np.ascontiguousarray(m) for m in members]
+        for m in self.members:
+            if m.size and (int(m.min()) < 0 or int(m.max()) >= self.n):
+                raise ValueError("class member ids out of range")
+        self.n_class = len(members)
+        self.fan = np.asarray(fanouts(dataset, nlayers), dtype=np.int32)
+        self.nh = len(self.fan)
+        self.batch = int(batch)
+        self.align = int(align)
+        self.labels = None if labels is None else labels.to(self.device, torch.int32).contiguous()
+        self.max_batch = int(min(batch, max(len(m) for m in self.members)))
+        self.side = torch.cuda.Stream(self.device)
+        with torch.cuda.device(self.device):
+            self.handle = self.lib.gs_dsampler_create(
+                self.n, adj_csr.rowptr.data_ptr(), adj_csr.col.data_ptr(), adj_csr.val.data_ptr(),
+                0 if self.labels is None else self.labels.data_ptr(), self.nh, self.fan.ctypes.data, self.n_class,
+                self.max_batch, self.align, self.side.cuda_stream)
+        if not self.handle:
+            raise _lib.GraphSlimLibraryError("gs_dsampler_create failed: " +
+                                             self.lib.gs_last_error().decode("utf-8", "replace"))
+        self.cap = int(self.lib.gs_dsampler_out_capacity(self.handle))
+        R = self.RING
+        self.ring = [torch.empty(self.cap, dtype=torch.uint8, device=self.device) for _ in range(R)]
+        self.desc_dev = [torch.empty(64, dtype=torch.int64, device=self.device) for _ in range(R)]
+        self.desc_host = [torch.empty(64, dtype=torch.int64).pin_memory() for _ in range(R)]
+        nb = self.n_class * self.max_batch + self.n_class + 1
+        self.batch_host = [torch.empty(nb, dtype=torch.int32).pin_memory() for _ in range(R)]
+        self.batch_dev = [torch.empty(nb, dtype=torch.int32, device=self.device) for _ in range(R)]
+        self.done = [None] * R                 # side-stream event: slot's blocks and desc are ready
+        self.consumed = [None] * R             # main-stream event: slot's previous blocks are no longer needed
+        self.slot = -1
+        self._mat_cache = {}
+        self._group_cache = {}
+        self.bytes_moved = 0
+        self.stats = dict(steps=0, draw_batches_ms=0.0, launch_ms=0.0, wait_ready_ms=0.0)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                torch.cuda.synchronize(self.device)
+                self.lib.gs_dsampler_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def set_labels(self, labels):
+        raise RuntimeError("pass labels to the constructor (the device sampler binds them at creation)")
+
+    # ---- random streams --------------------------------------------------------------------------
+    def draw_batches(self):
+        """np.random.permutation(class members)[:256] per class, in class order (loader.py:222)."""
+        parts = [np.random.permutation(m)[:self.batch].astype(np.int32) for m in self.members]
+        off = np.zeros(self.n_class + 1, dtype=np.int32)
+        off[1:] = np.cumsum([p.size for p in parts])
+        return np.concatenate(parts), off
+
+    def checkout_rng(self):
+        """torch's CPU generator -> device.  Nothing may draw from it until `checkin_rng`."""
+        with _TorchMt() as g:
+            _lib.check(self.lib.gs_dsampler_set_rng(self.handle, g.state.ctypes.data, int(g.left[0]), int(g.next[0]),
+                                                    self.side.cuda_stream), "gs_dsampler_set_rng")
+
+    def checkin_rng(self):
+        with _TorchMt() as g:
+            _lib.check(self.lib.gs_dsampler_get_rng(self.handle, g.state.ctypes.data, g.left.ctypes.data,
+                                                    g.next.ctypes.data, self.side.cuda_stream), "gs_dsampler_get_rng")
+
+    # ---- one step ----------------------------------------------------------------------------------
+    def _materialise_dev(self, materialise):
+        if materialise is None:
+            return None
+        key = tuple(int(m) for m in materialise)
+        t = self._mat_cache.get(key)
+        if t is None:
+            t = torch.tensor(key, dtype=torch.uint8, device=self.device)
+            self._mat_cache[key] = t
+        return t
+
+    def launch(self, batch, off, materialise=None):
+        """Queues the sampling of one step on the side stream; returns the ring slot."""
+        t0 = time.perf_counter()
+        self.slot = slot = (self.slot + 1) % self.RING
+        if self.done[slot] is not None:
+            self.done[slot].synchronize()             # the pinned staging of this slot is free again
+        nb = batch.size
+        hb = self.batch_host[slot]
+        hb[:nb] = torch.from_numpy(batch)
+        hb[nb:nb + off.size] = torch.from_numpy(off)
+        mat = self._materialise_dev(materialise)
+        with torch.cuda.stream(self.side):
+            if self.consumed[slot] is not None:
+                self.side.wait_event(self.consumed[slot])
+            db = self.batch_dev[slot]
+            db[:nb + off.size].copy_(hb[:nb + off.size], non_blocking=True)
+            _lib.check(self.lib.gs_dsampler_sample_step(
+                self.handle, self.n_class, db.data_ptr(), db.data_ptr() + 4 * nb, 0 if mat is None else mat.data_ptr(),
+                self.max_batch, self.ring[slot].data_ptr(), self.cap, self.desc_dev[slot].data_ptr(),
+                self.side.cuda_stream), "gs_dsampler_sample_step")
+            self.desc_host[slot].copy_(self.desc_dev[slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[slot] = ev
+        self.bytes_moved += 4 * (nb + off.size) + 512
+        self.stats["launch_ms"] += (time.perf_counter() - t0) * 1e3
+        return slot
+
+    def collect(self, slot, materialise=None):
+        """Waits for the slot's step, makes the current stream depend on it, returns the RealBatch of device views."""
+        t0 = time.perf_counter()
+        self.done[slot].synchronize()
+        desc = self.desc_host[slot].numpy().copy()
+        if desc[63] != 0:
+            raise _lib.GraphSlimLibraryError(f"device sampler: packed output does not fit ({int(desc[63])})")
+        torch.cuda.current_stream(self.device).wait_event(self.done[slot])
+        rb = self.unpack(self.ring[slot], desc, materialise)
+        rb.h2d_bytes = 0
+        rb.draws = int(desc[60])
+        self.stats["steps"] += 1
+        self.stats["wait_ready_ms"] += (time.perf_counter() - t0) * 1e3
+        return rb
+
+    def release(self, slot):
+        """Call once every consumer of the slot's views has been queued on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.consumed[slot] = ev
+
+    def sample(self, materialise=None):
+        """Synchronous step (tests, non-prefetched runs): both random streams advance exactly once."""
+        batch, off = self.draw_batches()
+        self.checkout_rng()
+        slot = self.launch(batch, off, materialise)
+        rb = self.collect(slot, materialise)
+        self.checkin_rng()
+        return rb
+
+    def prefetch(self, n_steps, materialise=None):
+        return _DevicePrefetcher(self, n_steps, materialise)
+
+
+class _DevicePrefetcher:
+    """Sampling of step i+1 runs on the side stream while step i is consumed.  A worker thread draws the class
+    batches (numpy releases the GIL inside the shuffle); the kernels are queued from the consumer's thread."""
+
+    def __init__(self, sampler, n_steps, materialise):
+        self.s, self.mat, self.n = sampler, materialise, n_steps
+        self.q = queue.Queue(maxsize=2)
+        self.stop = False
+        self.t = threading.Thread(target=self._draw, daemon=True)
+        self.t.start()
+        self.s.checkout_rng()
+        self.i = 0
+        self.prev_slot = None
+        self.slots = {}
+        if n_steps > 0:
+            self._launch(0)
+
+    def _draw(self):
+        try:
+            for _ in range(self.n):
+                t0 = time.perf_counter()
+                item = self.s.draw_batches()
+                self.s.stats["draw_batches_ms"] += (time.perf_counter() - t0) * 1e3
+                while not self.stop:
+                    try:
+                        self.q.put(item, timeout=0.05)
+                        break
+                    except queue.Full:
+                        continue
+                if self.stop:
+                    return
+        except BaseException as exc:
+            self.q.put(exc)
+
+    def _launch(self, i):
+        item = self.q.get()
+        if isinstance(item, BaseException):
+            raise item
+        self.slots[i] = self.s.launch(item[0], item[1], self.mat)
+
+    def next(self):
+        i = self.i
+        if self.prev_slot is not None:
+            self.s.release(self.prev_slot)       # everything that read step i-1's blocks is queued by now
+        if i + 1 < self.n:
+            self._launch(i + 1)
+        slot = self.slots.pop(i)
+        rb = self.s.collect(slot, self.mat)
+        self.prev_slot = slot
+        self.i += 1
+        return rb
+
+    def join(self):
+        if self.i < self.n:
+            self.stop = True                     # consumer failed mid-epoch: streams stay where they are
+        self.t.join(timeout=60)
+        self.stop = True
+        if self.prev_slot is not None:
+            self.s.release(self.prev_slot)
+            self.prev_slot = None
+        self.s.checkin_rng()

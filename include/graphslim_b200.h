@@ -144,6 +144,18 @@ int gs_dense_gcn_norm_bwd_f32(int32_t n, const float* dAhat, const float* Ahat, 
 int gs_pge_l1_stats_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, int32_t nchunk,
                         const int64_t* chunk_off, float eps, float* mean, float* rstd,
                         double* work /* 2*nchunk*h */, void* stream);
+/* Unchunked case (one BatchNorm batch over all n*n pairs): the statistics of Pa[j]+Pb[i] factorise exactly into the
+ * column statistics of Pa and Pb (mean = mean_a + mean_b, var = var_a + var_b), 2n rows read instead of n*n.
+ * col_mean (2 x h): column means of Pa and Pb, reused by gs_pge_bn1_bwd_closed_f32.  parametrized_adj.py:57-70. */
+int gs_pge_l1_stats_closed_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, float eps, float* mean,
+                               float* rstd, float* col_mean, void* stream);
+/* BN1 + ReLU backward of the factorised layer 1 in one pass over dH1 (unchunked): dPa[j] = sum_i dPre[(i,j)],
+ * dPb[i] = sum_j dPre[(i,j)], dgamma1, dbeta1 (autograd of parametrized_adj.py:57-66).
+ * work: 16-byte aligned, >= 16*h + 8*n*h bytes. */
+int gs_pge_bn1_bwd_closed_f32(int32_t n, int32_t h, const float* dH1, const float* Pa, const float* Pb,
+                              const float* mean, const float* rstd, const float* gamma, const float* beta,
+                              const float* col_mean, float* dPa, float* dPb, float* dgamma, float* dbeta, void* work,
+                              int64_t work_bytes, void* stream);
 /* H1[k,:] = relu(gamma*(Pa[j]+Pb[i]-mean)*rstd + beta) */
 int gs_pge_l1_expand_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, int32_t nchunk,
                          const int64_t* chunk_off, const float* mean, const float* rstd, const float* gamma,
@@ -215,6 +227,35 @@ gs_sample_job* gs_sampler_begin_step(gs_sampler* s, int32_t n_class, const int64
                                      const uint8_t* materialise, uint32_t* mt_state, int32_t* mt_left,
                                      int32_t* mt_next);
 int64_t gs_sampler_finish_step(gs_sampler* s, gs_sample_job* job, uint8_t* out, int64_t out_cap, int64_t* desc);
+
+/* ---- device-side class-batch neighbour sampler ---------------------------------------------
+ * Same contract as gs_sampler_* above (TransAndInd.retrieve_class_sampler, dataset/loader.py:187-224, with
+ * torch_geometric NeighborSampler / torch_sparse sample_adj under it), executed on the GPU against the CSR that is
+ * already in HBM: bit-identical class blocks for the same torch CPU generator state, no host sampling and no H2D copy
+ * of the blocks.  csrc/device_sampler.cu explains how the serial mt19937 stream and the unordered_set iteration order
+ * are reproduced in parallel.  All pointers are DEVICE pointers unless noted; work is queued on `stream`. */
+typedef struct gs_dsampler gs_dsampler;
+gs_dsampler* gs_dsampler_create(int32_t n_nodes, const int32_t* d_rowptr, const int32_t* d_col, const float* d_val,
+                                const int32_t* d_labels /* may be NULL */, int32_t n_hops,
+                                const int32_t* fanout /* host */, int32_t n_class_max, int32_t batch_max,
+                                int32_t align, void* stream);
+void gs_dsampler_destroy(gs_dsampler* s);
+/* bytes the packed output of one step can need / bytes of device scratch the handle owns */
+int64_t gs_dsampler_out_capacity(const gs_dsampler* s);
+int64_t gs_dsampler_scratch_bytes(const gs_dsampler* s);
+/* torch's mt19937 engine (624 state words, `left`, `next`; host pointers) <-> the device-resident generator.
+ * Both calls synchronise `stream`. */
+int gs_dsampler_set_rng(gs_dsampler* s, const uint32_t* state, int32_t left, int32_t next, void* stream);
+int gs_dsampler_get_rng(gs_dsampler* s, uint32_t* state, int32_t* left, int32_t* next, void* stream);
+/* One outer step for n_class classes: d_batch = concatenated class batches (int32 node ids), d_batch_off = n_class+1
+ * offsets, d_materialise = per-class 0/1 or NULL (class sharding: skipped classes still consume their random draws),
+ * max_batch = largest class batch (host value).  d_desc (64 x int64) receives the layout of d_out exactly as
+ * gs_sampler_finish_step's `desc`, plus [60] draws consumed, [62] bytes used, [63] 0 or GS_ENOSPC. */
+int gs_dsampler_sample_step(gs_dsampler* s, int32_t n_class, const int32_t* d_batch, const int32_t* d_batch_off,
+                            const uint8_t* d_materialise, int32_t max_batch, uint8_t* d_out, int64_t out_cap,
+                            int64_t* d_desc, void* stream);
+/* host-side check of the std::unordered_set iteration-order restatement used by the device sampler (tests) */
+int64_t gs_uset_emul_order(const int64_t* keys, int64_t n, int64_t* out);
 
 #ifdef __cplusplus
 }

@@ -153,4 +153,14 @@ void oracle_spmm_csr_f32(int64_t n_rows, const int64_t* rowptr, const int64_t* c
   }
 }
 
+// Iteration order of the real std::unordered_set<int64_t> after inserting keys[0..n) (duplicates ignored):
+// pins the container restatement the device sampler uses.  Returns the number of distinct keys.
+int64_t oracle_uset_order(const int64_t* keys, int64_t n, int64_t* out) {
+  std::unordered_set<int64_t> s;
+  for (int64_t i = 0; i < n; ++i) s.insert(keys[i]);
+  int64_t m = 0;
+  for (const int64_t& k : s) out[m++] = k;
+  return m;
+}
+
 }  // extern "C"

@@ -53,6 +53,8 @@ def lib():
         L.oracle_sample_adj.restype = ctypes.c_int64
         L.oracle_spmm_csr_f32.argtypes = [ctypes.c_int64, i64p, i64p, f32p, f32p, ctypes.c_int64, f32p]
         L.oracle_spmm_csr_f32.restype = None
+        L.oracle_uset_order.argtypes = [i64p, ctypes.c_int64, i64p]
+        L.oracle_uset_order.restype = ctypes.c_int64
         _lib = L
     return _lib
 

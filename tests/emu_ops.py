@@ -224,6 +224,20 @@ class EmuOps:
     def pge_l1_stats(self, Pa, Pb, chunk_off, eps=1e-5):
         return self._stats(self._y1(Pa, Pb), chunk_off, eps)
 
+    def pge_l1_stats_closed(self, Pa, Pb, eps=1e-5):
+        a, b = Pa.double(), Pb.double()
+        var = a.var(0, unbiased=False) + b.var(0, unbiased=False)
+        mean = a.mean(0) + b.mean(0)
+        return (mean.float().view(1, -1), (1.0 / torch.sqrt(var + eps)).float().view(1, -1),
+                torch.stack([a.mean(0), b.mean(0)]).float())
+
+    def pge_bn1_bwd_closed(self, dH1, Pa, Pb, mean, rstd, gamma, beta, col_mean):
+        n = Pa.shape[0]
+        off = torch.tensor([0, n * n])
+        s1, s2 = self.pge_bn1_bwd_stats(dH1, Pa, Pb, off, mean, rstd, gamma, beta)
+        dPa, dPb = self.pge_bn1_bwd_reduce(dH1, Pa, Pb, off, mean, rstd, gamma, beta, s1, s2)
+        return dPa, dPb, s2.sum(0), s1.sum(0)
+
     def pge_l1_expand(self, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
         y = self._y1(Pa, Pb)
         rows = y.shape[0]

@@ -15,7 +15,7 @@ def declared_functions():
     text = open(os.path.join(ROOT, "include", "graphslim_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(?:int|int64_t|void|const char\*|gs_sampler\*|gs_sample_job\*)\s+\*?(gs_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"\b(?:int|int64_t|void|const char\*|gs_sampler\*|gs_sample_job\*|gs_dsampler\*)\s+\*?(gs_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
         name, params = m.group(1), m.group(2).strip()
         n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
         out[name] = n

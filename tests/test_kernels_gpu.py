@@ -304,3 +304,36 @@ def test_pge_kernels(K, E, n, h, nchunk):
 def test_cpu_tensors_are_rejected(K):
     with pytest.raises((TypeError, ValueError, RuntimeError)):
         K.gemm(torch.randn(4, 4), torch.randn(4, 4))
+
+
+@pytest.mark.parametrize("n,h", [(23, 128), (61, 256), (40, 64)])
+def test_pge_unchunked_fast_paths(K, E, n, h):
+    """Closed-form BN1 statistics, one-pass BN1 backward and the register-resident layer-3 kernel against the generic
+    per-chunk kernels' reference."""
+    gen = torch.Generator().manual_seed(7 * n + h)
+    total = n * n
+    off = torch.tensor([0, total], dtype=torch.int64)
+    Pa = torch.randn(n, h, generator=gen) * 1.5 + 0.3
+    Pb = torch.randn(n, h, generator=gen) - 0.7
+    gamma = torch.rand(h, generator=gen) + 0.5
+    beta = torch.randn(h, generator=gen) * 0.1
+    c = lambda t: t.cuda()
+    m1r, r1r = E.pge_l1_stats(Pa, Pb, off)
+    m1, r1, cm = K.pge_l1_stats_closed(c(Pa), c(Pb))
+    close(m1, m1r, rtol=1e-5)
+    close(r1, r1r, rtol=1e-5)
+    close(cm, torch.stack([Pa.double().mean(0), Pb.double().mean(0)]).float(), rtol=1e-5)
+    dH1 = torch.randn(total, h, generator=gen)
+    t1r, t2r = E.pge_bn1_bwd_stats(dH1, Pa, Pb, off, m1r, r1r, gamma, beta)
+    dPar, dPbr = E.pge_bn1_bwd_reduce(dH1, Pa, Pb, off, m1r, r1r, gamma, beta, t1r, t2r)
+    dPa, dPb, dg, db = K.pge_bn1_bwd_closed(c(dH1), c(Pa), c(Pb), c(m1r), c(r1r), c(gamma), c(beta), cm)
+    close(dPa, dPar, rtol=1e-4)
+    close(dPb, dPbr, rtol=1e-4)
+    close(dg, t2r.sum(0), rtol=1e-4)
+    close(db, t1r.sum(0), rtol=1e-4)
+    Y2 = torch.randn(total, h, generator=gen) * 2 + 1
+    m2r, r2r = E.col_stats_chunked(Y2, off)
+    w3 = torch.randn(h, generator=gen) * 0.1
+    b3 = torch.randn(1, generator=gen)
+    Ek = K.pge_l3(c(Y2), c(off), c(m2r), c(r2r), c(gamma), c(beta), c(w3), c(b3))
+    close(Ek, E.pge_l3(Y2, off, m2r, r2r, gamma, beta, w3, b3), rtol=1e-4)

@@ -76,6 +76,7 @@ SIGNATURES = {
     "gs_dsampler_get_rng": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gs_dsampler_sample_step": (c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp]),
     "gs_uset_emul_order": (c_i64, [c_vp, c_i64, c_vp]),
+    "gs_dsampler_debug_counters": (c_int, [c_vp, c_vp, c_vp]),
 }
 
 _lib = None

@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src + ".o")
-        flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+        flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("GS_NVCC_EXTRA", "").split()
         cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

@@ -9,7 +9,7 @@
 // What makes the reference's index selection reproducible in parallel:
 //   * torch::randint(0, j) on the CPU generator is the next mt19937 word % j.  The raw (untempered) state blocks of
 //     the generator are produced ahead of time by one CTA (mt_generate_kernel: 624-word blocks, three dependent
-//     phases each), so draw number p of the step is a plain array read (stream_word);
+//     phases each), so draw number p of the step is a plain array read (stream_raw);
 //   * a row consumes `fanout` draws iff degree > fanout, so the draw offset of every row is a prefix sum over degrees;
 //   * the order in which a row's chosen neighbours are appended to n_id is the iteration order of libstdc++'s
 //     unordered_set, restated in uset_emul.h (one thread per row, <= 15 keys);
@@ -32,7 +32,7 @@ namespace gs {
 namespace ds {
 
 constexpr int kMaxHops = 5;
-constexpr int kThreads = 1024;
+constexpr int kThreads = 512;             // 128 registers per thread: the per-row arrays stay out of local memory
 constexpr int kWarps = kThreads / 32;
 constexpr int kCursorSmemInts = 40 * 1024;       // transposed-block cursors kept in shared memory up to this many columns
 
@@ -61,6 +61,8 @@ struct Ptrs {
   int32_t* nid;              // [class][lcap[nh]]
   int32_t* level_count;      // [class][nh+1]
   int64_t* last_off;         // [class]       stream offset of the class's last hop
+  int64_t* hop_off;          // [class]       stream offset of the hop before the last one
+  long long* hop_tot;        // [class]       (draws << 32 | candidates) of that hop (phase 1), or the last hop's draws when nh == 1
   int32_t* rowoff[kMaxHops];   // [class][lcap[h]+1]  CSR row pointer of the class block
   int32_t* drawoff[kMaxHops];  // [class][lcap[h]]
   int32_t* cand_e[kMaxHops];   // [class][ncap[h]]    sampled edge ids in discovery order
@@ -74,6 +76,7 @@ struct Ptrs {
   int32_t* t_cursor;           // [class][lcap[nh]]   fallback cursors when the columns do not fit in shared memory
   int32_t* seg;                // [(nh+1)][n_class+1] padded level offsets of the batch
   int64_t* eoff;               // [nh][n_class+1]     edge offsets of the batch
+  long long* dbg;              // [16] phase cycle counters of the serial kernel (GS_DS_PROFILE builds)
 };
 
 // ------------------------------------------------------------------------------------------ mt19937 stream
@@ -130,15 +133,6 @@ __global__ void __launch_bounds__(256) mt_generate_kernel(const MtDev* __restric
   }
 }
 
-// tempered output number p (0-based) of the step's stream
-__device__ __forceinline__ uint32_t stream_word(const uint32_t* __restrict__ R, int rem0, int next0, int64_t p) {
-  uint32_t y = (p < rem0) ? R[next0 + p] : R[624 + (p - rem0)];
-  y ^= y >> 11;
-  y ^= (y << 7) & 0x9d2c5680u;
-  y ^= (y << 15) & 0xefc60000u;
-  return y ^ (y >> 18);
-}
-
 // ------------------------------------------------------------------------------------------ block-wide scans
 // exclusive prefix sums of f(i), i in [0, m), in index order; emit(i, prefix, f(i)); returns the total to every thread.
 // sm: kWarps + 1 elements of shared memory.
@@ -165,7 +159,7 @@ __device__ __forceinline__ T block_scan(int m, F f, E emit, T* sm) {
         const T t = __shfl_up_sync(0xffffffffu, w, o);
         if (lane >= o) w += t;
       }
-      sm[lane] = w;
+      if (lane < nwarps) sm[lane] = w;
     }
     __syncthreads();
     const T wpre = warp > 0 ? sm[warp - 1] : (T)0;
@@ -179,24 +173,148 @@ __device__ __forceinline__ T block_scan(int m, F f, E emit, T* sm) {
 
 // ------------------------------------------------------------------------------------------ one hop of one class
 // Rows = the class's nodes discovered so far (nid[0..n_rows)).  Returns the new node count; *draws = words consumed.
-__device__ int do_hop(const Geom& G, const Ptrs& P, int c, int h, bool record, int64_t draw_base, int rem0, int next0,
-                      int n_rows, long long* draws, long long* sm) {
+// Every per-row step first issues all of its independent loads (stream words, column ids, pos entries, values) into
+// register arrays and only then consumes them: the kernel is a chain of dependent global round trips, so the number of
+// round trips per hop, not bandwidth, sets its duration.
+constexpr int KM = 15;   // largest fan-out (checked at creation)
+
+#ifdef GS_DS_PROFILE
+#define GS_TICK(i)                                                            \
+  do {                                                                        \
+    if (threadIdx.x == 0 && gridDim.x == 1) {                                 \
+      const long long now_ = clock64();                                       \
+      P.dbg[i] += now_ - tick_;                                               \
+      tick_ = now_;                                                           \
+    }                                                                         \
+  } while (0)
+#else
+#define GS_TICK(i)
+#endif
+
+__device__ __forceinline__ uint32_t stream_raw(const uint32_t* __restrict__ R, int rem0, int next0, int64_t p) {
+  return (p < rem0) ? R[next0 + p] : R[624 + (p - rem0)];
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  return y ^ (y >> 18);
+}
+
+// The container restatement of uset_emul.h with its arrays in SHARED memory (word i of thread t at smem[i*blockDim+t]:
+// every lane stays in its own bank whatever it indexes).  In local memory the dynamically indexed key / next / bucket
+// arrays miss L1 (most of it is carved out as shared memory here) and every one of the ~10^3 dependent accesses per
+// row becomes an L2 round trip -- measured: 100 us per row batch instead of a few.
+struct USetSm {
+  static constexpr int kWords = 36;        // 16 keys + 4 (16 x int8 next) + 2 x 8 (32 x int8 buckets, double buffered)
+  static constexpr int kNil = -1, kEmpty = -2, kBeforeBegin = -3;
+  uint32_t* base;
+  int stride;
+  int head, nb, cnt, next_resize, boff;
+
+  __device__ __forceinline__ USetSm(uint32_t* smem) : base(smem + threadIdx.x), stride(blockDim.x) {}
+  __device__ __forceinline__ int key(int i) const { return (int)base[i * stride]; }
+  __device__ __forceinline__ void set_key(int i, int v) { base[i * stride] = (uint32_t)v; }
+  __device__ __forceinline__ int get8(int off, int i) const {
+    const uint32_t w = base[(off + (i >> 2)) * stride];
+    return (int)(int8_t)((w >> ((i & 3) * 8)) & 0xffu);
+  }
+  __device__ __forceinline__ void set8(int off, int i, int v) {
+    uint32_t* p = base + (off + (i >> 2)) * stride;
+    const int sh = (i & 3) * 8;
+    *p = (*p & ~(0xffu << sh)) | (((uint32_t)v & 0xffu) << sh);
+  }
+  __device__ __forceinline__ int nxt(int i) const { return get8(16, i); }
+  __device__ __forceinline__ void set_nxt(int i, int v) { set8(16, i, v); }
+  __device__ __forceinline__ void fill_buckets(int off) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) base[(off + w) * stride] = 0xfefefefeu;      // kEmpty in every byte
+  }
+  __device__ __forceinline__ void clear() {
+    nb = 1;
+    cnt = 0;
+    next_resize = 0;
+    head = kNil;
+    boff = 20;
+    fill_buckets(boff);
+  }
+  __device__ __forceinline__ int next_of(int node) const { return node == kBeforeBegin ? head : nxt(node); }
+  __device__ __forceinline__ void set_next(int node, int v) {
+    if (node == kBeforeBegin) head = v;
+    else set_nxt(node, v);
+  }
+  __device__ __forceinline__ int next_bkt(int n) {
+    int r;
+    if (n <= 13) r = n <= 2 ? 2 : (n == 3 ? 3 : (n <= 5 ? 5 : (n <= 7 ? 7 : (n <= 11 ? 11 : 13))));
+    else r = n <= 17 ? 17 : (n <= 19 ? 19 : (n <= 23 ? 23 : (n <= 29 ? 29 : (n <= 31 ? 31 : 37))));
+    next_resize = r;
+    return r;
+  }
+  __device__ __forceinline__ void rehash(int n) {
+    const int noff = boff == 20 ? 28 : 20;
+    fill_buckets(noff);
+    int p = head;
+    head = kNil;
+    int bbegin_bkt = 0;
+    while (p != kNil) {
+      const int nx = nxt(p);
+      const int b = key(p) % n;
+      const int cur = get8(noff, b);
+      if (cur == kEmpty) {
+        set_nxt(p, head);
+        const int old_head = head;
+        head = p;
+        set8(noff, b, kBeforeBegin);
+        if (old_head != kNil) set8(noff, bbegin_bkt, p);
+        bbegin_bkt = b;
+      } else {
+        set_nxt(p, next_of(cur));
+        set_next(cur, p);
+      }
+      p = nx;
+    }
+    boff = noff;
+    nb = n;
+  }
+  __device__ __forceinline__ bool insert(int k) {
+    bool found = false;
+    for (int i = 0; i < cnt; ++i) found |= (key(i) == k);
+    if (found) return false;
+    if (cnt + 1 > next_resize) {
+      int min_bkts = cnt + 1;
+      if (next_resize == 0 && min_bkts < 11) min_bkts = 11;
+      if (min_bkts >= nb) {
+        const int want = (min_bkts + 1 > nb * 2) ? min_bkts + 1 : nb * 2;
+        rehash(next_bkt(want));
+      } else {
+        next_resize = nb;
+      }
+    }
+    const int b = k % nb;
+    const int node = cnt;
+    set_key(node, k);
+    const int cur = get8(boff, b);
+    if (cur != kEmpty) {
+      set_nxt(node, next_of(cur));
+      set_next(cur, node);
+    } else {
+      set_nxt(node, head);
+      if (head != kNil) set8(boff, key(head) % nb, node);
+      head = node;
+      set8(boff, b, kBeforeBegin);
+    }
+    ++cnt;
+    return true;
+  }
+};
+
+// phase 1 of a hop: candidates and draws per row -> offsets.  Returns (draws << 32 | candidates).
+__device__ long long hop_phase1(const Geom& G, const Ptrs& P, int c, int h, int n_rows, long long* sm) {
   const int k = G.fan[h];
-  const bool last = (h == G.nh - 1);
-  int32_t* nid = P.nid + (int64_t)c * G.lcap[G.nh];
-  int32_t* pos = P.pos + (int64_t)c * G.n;
-  int32_t* firstq = P.firstq + (int64_t)c * G.n;
+  const int32_t* nid = P.nid + (int64_t)c * G.lcap[G.nh];
   int32_t* rowoff = P.rowoff[h] + (int64_t)c * (G.lcap[h] + 1);
   int32_t* drawoff = P.drawoff[h] + (int64_t)c * G.lcap[h];
-  int32_t* cand_e = P.cand_e[h] + (int64_t)c * G.ncap[h];
-  int32_t* cand_u = P.cand_u[h] + (int64_t)c * G.ncap[h];
-  int32_t* ocol = P.ocol[h] + (int64_t)c * G.ncap[h];
-  float* oval = P.oval[h] + (int64_t)c * G.ncap[h];
-  int32_t* erow = P.erow[h] + (int64_t)c * G.ncap[h];
   const int32_t* __restrict__ rp = P.rowptr;
-  const int32_t* __restrict__ gcolp = P.col;
-
-  // phase 1: candidates and draws per row -> offsets (high word: draws, low word: candidates)
   const long long tot = block_scan<long long>(
       n_rows,
       [&](int t) {
@@ -211,45 +329,202 @@ __device__ int do_hop(const Geom& G, const Ptrs& P, int c, int h, bool record, i
         drawoff[t] = (int32_t)(pre >> 32);
       },
       sm);
-  const int n_cand = (int)(tot & 0xffffffffll);
-  *draws = tot >> 32;
-  if (threadIdx.x == 0) rowoff[n_rows] = n_cand;
+  if (threadIdx.x == 0) rowoff[n_rows] = (int32_t)(tot & 0xffffffffll);
   __syncthreads();
+  return tot;
+}
+
+// Few rows (the hops of the serial kernel): spread them over all warps so divergent lanes serialise less.
+struct RowMap {
+  bool active;
+  int first, step;
+  __device__ __forceinline__ RowMap(int n_rows) {
+    int spread = 1;
+    while (spread < 32 && n_rows * spread * 2 <= (int)blockDim.x) spread *= 2;
+    active = (threadIdx.x % spread) == 0;
+    first = threadIdx.x / spread;
+    step = blockDim.x / spread;
+  }
+};
+
+// "Light" hop: what the NEXT class's stream offset needs from this hop, and nothing else.  The words a row consumes are
+// fixed by the row order (phase 1); which nodes the hop discovers does not depend on the container's iteration order,
+// so the chain only has to (1) turn words into Floyd positions, (2) read their column ids, (3) find the distinct new
+// nodes (atomicMin marker on firstq; pos/nid stay untouched) and (4) add up (degree > k_next ? k_next : 0) over the
+// rows and the new nodes = the number of words the next hop will consume.  The full hop (ordering, relabelling, block
+// emission) is redone later by the class-parallel kernel, which first clears the markers through cand_u.
+__device__ long long light_hop(const Geom& G, const Ptrs& P, int c, int h, int64_t draw_base, int rem0, int next0,
+                               int n_rows, int k_next, long long* sm) {
+  const int k = G.fan[h];
+  const int32_t* nid = P.nid + (int64_t)c * G.lcap[G.nh];
+  const int32_t* pos = P.pos + (int64_t)c * G.n;
+  int32_t* firstq = P.firstq + (int64_t)c * G.n;
+  const int32_t* rowoff = P.rowoff[h] + (int64_t)c * (G.lcap[h] + 1);
+  const int32_t* drawoff = P.drawoff[h] + (int64_t)c * G.lcap[h];
+  int32_t* cand_u = P.cand_u[h] + (int64_t)c * G.ncap[h];
+  const int32_t* __restrict__ rp = P.rowptr;
+  const int32_t* __restrict__ gcolp = P.col;
+  long long mine = 0;
+  const RowMap rm(n_rows);
+  for (int t = rm.first; rm.active && t < n_rows; t += rm.step) {
+    const int v = nid[t];
+    const int q0 = rowoff[t];
+    const int64_t d0 = draw_base + drawoff[t];
+    const int beg = rp[v], deg = rp[v + 1] - beg;
+    if (deg > k_next) mine += k_next;
+    int pk[KM];
+    int cnt;
+    if (deg <= k) {
+      cnt = deg;
+#pragma unroll
+      for (int i = 0; i < KM; ++i) pk[i] = i;
+    } else {
+      cnt = k;
+      uint32_t w[KM];
+#pragma unroll
+      for (int i = 0; i < KM; ++i) w[i] = (i < k) ? stream_raw(P.R, rem0, next0, d0 + i) : 0u;
+#pragma unroll
+      for (int i = 0; i < KM; ++i) {
+        pk[i] = 0;
+        if (i < k) {
+          const int j = deg - k + i;
+          const int r = (int)(mt_temper(w[i]) % (uint32_t)j);
+          bool dup = false;
+#pragma unroll
+          for (int e = 0; e < i; ++e) dup |= (pk[e] == r);
+          pk[i] = dup ? j : r;
+        }
+      }
+    }
+    int u[KM], old[KM], ps[KM];
+#pragma unroll
+    for (int i = 0; i < KM; ++i) u[i] = (i < cnt) ? gcolp[beg + pk[i]] : 0;
+#pragma unroll
+    for (int i = 0; i < KM; ++i) {
+      old[i] = 0;
+      ps[i] = 0;
+      if (i < cnt) {
+        old[i] = atomicMin(&firstq[u[i]], -1);
+        ps[i] = pos[u[i]];
+        cand_u[q0 + i] = u[i];
+      }
+    }
+    int dg[KM];
+#pragma unroll
+    for (int i = 0; i < KM; ++i) {
+      const bool fresh = (i < cnt) && old[i] == INT_MAX && ps[i] < 0;
+      dg[i] = fresh ? (rp[u[i] + 1] - rp[u[i]]) : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < KM; ++i)
+      if (dg[i] > k_next) mine += k_next;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (threadIdx.x == 0) sm[kWarps] = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(reinterpret_cast<unsigned long long*>(&sm[kWarps]), (unsigned long long)mine);
+  __syncthreads();
+  const long long total = sm[kWarps];
+  __syncthreads();
+  return total;
+}
+
+// Full hop.  have_phase1: the row offsets (and stale light-hop markers, cleared here through cand_u) already exist.
+__device__ int do_hop(const Geom& G, const Ptrs& P, int c, int h, bool record, bool have_phase1, int64_t draw_base,
+                      int rem0, int next0, int n_rows, long long* draws, long long* sm, uint32_t* uset_sm) {
+  const int k = G.fan[h];
+  const bool last = (h == G.nh - 1);
+  int32_t* nid = P.nid + (int64_t)c * G.lcap[G.nh];
+  int32_t* pos = P.pos + (int64_t)c * G.n;
+  int32_t* firstq = P.firstq + (int64_t)c * G.n;
+  int32_t* rowoff = P.rowoff[h] + (int64_t)c * (G.lcap[h] + 1);
+  int32_t* drawoff = P.drawoff[h] + (int64_t)c * G.lcap[h];
+  int32_t* cand_e = P.cand_e[h] + (int64_t)c * G.ncap[h];
+  int32_t* cand_u = P.cand_u[h] + (int64_t)c * G.ncap[h];
+  int32_t* ocol = P.ocol[h] + (int64_t)c * G.ncap[h];
+  float* oval = P.oval[h] + (int64_t)c * G.ncap[h];
+  int32_t* erow = P.erow[h] + (int64_t)c * G.ncap[h];
+  const int32_t* __restrict__ rp = P.rowptr;
+  const int32_t* __restrict__ gcolp = P.col;
+#ifdef GS_DS_PROFILE
+  long long tick_ = clock64();
+#endif
+
+  int n_cand;
+  if (have_phase1) {
+    n_cand = rowoff[n_rows];
+    *draws = 0;
+    for (int q = threadIdx.x; q < n_cand; q += blockDim.x) firstq[cand_u[q]] = INT_MAX;
+    __syncthreads();
+  } else {
+    const long long tot = hop_phase1(G, P, c, h, n_rows, sm);
+    n_cand = (int)(tot & 0xffffffffll);
+    *draws = tot >> 32;
+  }
+  GS_TICK(0);
 
   // phase 2: Robert-Floyd draws into the container restatement; candidates in the container's iteration order
-  for (int t = threadIdx.x; t < n_rows; t += blockDim.x) {
+  const RowMap rm(n_rows);
+  const bool row_thread = rm.active;
+  const int row_first = rm.first, row_step = rm.step;
+  for (int t = row_first; row_thread && t < n_rows; t += row_step) {
     const int v = nid[t];
+    const int q0 = rowoff[t];
+    const int64_t d0 = draw_base + drawoff[t];
     const int beg = rp[v], deg = rp[v + 1] - beg;
-    USetEmul S;
+    USetSm S(uset_sm);
     S.clear();
     if (deg <= k) {
       for (int j = 0; j < deg; ++j) S.insert(j);
     } else {
-      const int64_t d0 = draw_base + drawoff[t];
-      for (int j = deg - k; j < deg; ++j) {
-        const uint32_t w = stream_word(P.R, rem0, next0, d0 + (j - (deg - k)));
-        const int r = (int)(w % (uint32_t)j);
-        if (!S.insert(r)) S.insert(j);
+      uint32_t w[KM];
+#pragma unroll
+      for (int i = 0; i < KM; ++i) w[i] = (i < k) ? stream_raw(P.R, rem0, next0, d0 + i) : 0u;
+#pragma unroll
+      for (int i = 0; i < KM; ++i) {
+        if (i < k) {
+          const int j = deg - k + i;
+          const int r = (int)(mt_temper(w[i]) % (uint32_t)j);
+          if (!S.insert(r)) S.insert(j);
+        }
       }
     }
-    int q = rowoff[t];
-    for (int p = S.head; p != USetEmul::kNil; p = S.nxt[p]) {
-      const int e = beg + S.key[p];
-      const int u = gcolp[e];
-      cand_e[q] = e;
-      cand_u[q] = u;
-      if (pos[u] < 0) atomicMin(&firstq[u], q);
-      ++q;
+    int keys[KM];
+    const int cnt = S.cnt;
+    int p = S.head;
+#pragma unroll
+    for (int i = 0; i < KM; ++i) {
+      keys[i] = 0;
+      if (i < cnt) {
+        keys[i] = S.key(p);
+        p = S.nxt(p);
+      }
+    }
+    int u[KM], ps[KM];
+#pragma unroll
+    for (int i = 0; i < KM; ++i) u[i] = (i < cnt) ? gcolp[beg + keys[i]] : 0;
+#pragma unroll
+    for (int i = 0; i < KM; ++i) ps[i] = (i < cnt) ? pos[u[i]] : 0;
+#pragma unroll
+    for (int i = 0; i < KM; ++i) {
+      if (i < cnt) {
+        cand_e[q0 + i] = beg + keys[i];
+        cand_u[q0 + i] = u[i];
+        if (ps[i] < 0) atomicMin(&firstq[u[i]], q0 + i);
+      }
     }
   }
   __syncthreads();
+  GS_TICK(1);
 
   // phase 3: first occurrences get the next class-local ids, in candidate order
   const long long n_new = block_scan<long long>(
       n_cand,
       [&](int q) {
         const int u = cand_u[q];
-        return (long long)((pos[u] < 0 && firstq[u] == q) ? 1 : 0);
+        const int pu = pos[u], fq = firstq[u];
+        return (long long)((pu < 0 && fq == q) ? 1 : 0);
       },
       [&](int q, long long pre, long long isnew) {
         if (isnew) {
@@ -261,84 +536,124 @@ __device__ int do_hop(const Geom& G, const Ptrs& P, int c, int h, bool record, i
       },
       sm);
   __syncthreads();
+  GS_TICK(2);
 
-  // phase 4: relabel, sort every row by local column, emit the class block
-  for (int t = threadIdx.x; t < n_rows; t += blockDim.x) {
+  // phase 4: relabel and emit the class block with every row sorted by local column.  The locals of a row are
+  // distinct, so an entry's place is its rank among the row's locals (all-pairs compare, no data-dependent loop).
+  for (int t = row_first; row_thread && t < n_rows; t += row_step) {
     const int q0 = rowoff[t], cnt = rowoff[t + 1] - q0;
-    int loc[USetEmul::kMax], ee[USetEmul::kMax];
-    for (int i = 0; i < cnt; ++i) {
-      const int u = cand_u[q0 + i];
-      loc[i] = pos[u];
-      ee[i] = cand_e[q0 + i];
-      firstq[u] = INT_MAX;
+    int cu[KM], ce[KM], loc[KM];
+    float vv[KM];
+#pragma unroll
+    for (int i = 0; i < KM; ++i) {
+      cu[i] = (i < cnt) ? cand_u[q0 + i] : 0;
+      ce[i] = (i < cnt) ? cand_e[q0 + i] : 0;
     }
+#pragma unroll
+    for (int i = 0; i < KM; ++i) {
+      loc[i] = (i < cnt) ? pos[cu[i]] : INT_MAX;
+      vv[i] = (i < cnt && record) ? P.val[ce[i]] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < KM; ++i)
+      if (i < cnt) firstq[cu[i]] = INT_MAX;
     if (!record) continue;
-    for (int i = 1; i < cnt; ++i) {
-      const int l = loc[i], e = ee[i];
-      int j = i - 1;
-      while (j >= 0 && loc[j] > l) {
-        loc[j + 1] = loc[j];
-        ee[j + 1] = ee[j];
-        --j;
+#pragma unroll
+    for (int i = 0; i < KM; ++i) {
+      if (i < cnt) {
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < KM; ++j) rank += (loc[j] < loc[i]) ? 1 : 0;
+        ocol[q0 + rank] = loc[i];
+        oval[q0 + rank] = vv[i];
+        erow[q0 + rank] = t;
+        if (last) ce[i] = rank;                    // remember where the entry went (cand_u is rewritten below)
       }
-      loc[j + 1] = l;
-      ee[j + 1] = e;
     }
-    for (int i = 0; i < cnt; ++i) {
-      ocol[q0 + i] = loc[i];
-      oval[q0 + i] = P.val[ee[i]];
-      erow[q0 + i] = t;
-      if (last) cand_u[q0 + i] = gcolp[ee[i]];     // global column ids of the outermost hop (fused feature gather)
+    if (last) {                                    // global column ids of the outermost hop (fused feature gather)
+#pragma unroll
+      for (int i = 0; i < KM; ++i)
+        if (i < cnt) cand_u[q0 + ce[i]] = cu[i];
     }
   }
   __syncthreads();
+  GS_TICK(3);
   return n_rows + (int)n_new;
 }
 
-// ------------------------------------------------------------------------------------------ serial part (1 CTA)
-__global__ void __launch_bounds__(kThreads)
-sample_serial_kernel(Geom G, Ptrs P, int n_class, const int32_t* __restrict__ batch,
-                     const int32_t* __restrict__ batch_off, const uint8_t* __restrict__ materialise) {
-  __shared__ long long sm[kWarps + 1];
-  __shared__ long long s_red;
-  const int rem0 = (int)P.step_info[1], next0 = (int)P.step_info[2];
-  long long draw_base = 0;
+// ------------------------------------------------------------------------------------------ per-class preparation
+// Class-parallel and independent of the random stream: batch -> n_id / pos map, and (two-hop case) the row offsets of
+// hop 0, which only depend on degrees.  For a single hop the only thing the serial kernel needs is the draw count.
+__global__ void __launch_bounds__(kThreads, 1)
+sample_prep_kernel(Geom G, Ptrs P, int n_class, const int32_t* __restrict__ batch,
+                   const int32_t* __restrict__ batch_off) {
+  __shared__ long long sm[kWarps + 2];
+  const int c = blockIdx.x;
+  if (c >= n_class) return;
+  int32_t* nid = P.nid + (int64_t)c * G.lcap[G.nh];
+  int32_t* pos = P.pos + (int64_t)c * G.n;
+  int32_t* lc = P.level_count + (int64_t)c * (G.nh + 1);
+  const int b0 = batch_off[c];
+  const int n_rows = batch_off[c + 1] - b0;
   const int k_last = G.fan[G.nh - 1];
+  long long mine = 0;
+  for (int t = threadIdx.x; t < n_rows; t += blockDim.x) {
+    const int v = batch[b0 + t];
+    nid[t] = v;
+    pos[v] = t;
+    if (G.nh == 1 && P.rowptr[v + 1] - P.rowptr[v] > k_last) mine += k_last;
+  }
+  if (threadIdx.x == 0) lc[0] = n_rows;
+  __syncthreads();
+  if (G.nh == 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (threadIdx.x == 0) sm[kWarps] = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(reinterpret_cast<unsigned long long*>(&sm[kWarps]), (unsigned long long)mine);
+    __syncthreads();
+    if (threadIdx.x == 0) P.hop_tot[c] = sm[kWarps];
+  } else if (G.nh == 2) {
+    const long long tot = hop_phase1(G, P, c, 0, n_rows, sm);
+    if (threadIdx.x == 0) P.hop_tot[c] = tot;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ serial part (1 CTA)
+// Cuts the random stream into per-class, per-hop segments.  Per class: full hops 0..nh-3 (only for three or more
+// hops: their exact n_id order fixes the next hop's row offsets), then the light version of hop nh-2, whose result is
+// the number of words hop nh-1 will consume.  Hops nh-2 and nh-1 themselves run class-parallel afterwards.
+__global__ void __launch_bounds__(kThreads, 1)
+sample_serial_kernel(Geom G, Ptrs P, int n_class, const uint8_t* __restrict__ materialise) {
+  extern __shared__ uint32_t uset_sm[];
+  __shared__ long long sm[kWarps + 2];
+#ifdef GS_DS_PROFILE
+  const long long t_begin = clock64();
+#endif
+  const int rem0 = (int)P.step_info[1], next0 = (int)P.step_info[2];
+  const int nh = G.nh;
+  long long draw_base = 0;
   for (int c = 0; c < n_class; ++c) {
     const bool keep = materialise == nullptr || materialise[c] != 0;
-    int32_t* nid = P.nid + (int64_t)c * G.lcap[G.nh];
-    int32_t* pos = P.pos + (int64_t)c * G.n;
-    int32_t* lc = P.level_count + (int64_t)c * (G.nh + 1);
-    const int b0 = batch_off[c];
-    int n_rows = batch_off[c + 1] - b0;
-    for (int t = threadIdx.x; t < n_rows; t += blockDim.x) {
-      const int v = batch[b0 + t];
-      nid[t] = v;
-      pos[v] = t;
+    int32_t* lc = P.level_count + (int64_t)c * (nh + 1);
+    int n_rows = lc[0];
+    if (nh == 1) {
+      if (threadIdx.x == 0) P.last_off[c] = draw_base;
+      draw_base += P.hop_tot[c];
+      continue;
     }
-    if (threadIdx.x == 0) lc[0] = n_rows;
-    __syncthreads();
-    for (int h = 0; h + 1 < G.nh; ++h) {
+    for (int h = 0; h + 2 < nh; ++h) {
       long long dr;
-      n_rows = do_hop(G, P, c, h, keep, draw_base, rem0, next0, n_rows, &dr, sm);
+      n_rows = do_hop(G, P, c, h, keep, false, draw_base, rem0, next0, n_rows, &dr, sm, uset_sm);
       draw_base += dr;
       if (threadIdx.x == 0) lc[h + 1] = n_rows;
     }
-    // segment of the stream that the class's last hop will consume
-    long long mine = 0;
-    for (int t = threadIdx.x; t < n_rows; t += blockDim.x) {
-      const int v = nid[t];
-      if (P.rowptr[v + 1] - P.rowptr[v] > k_last) mine += k_last;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if (threadIdx.x == 0) s_red = 0;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(reinterpret_cast<unsigned long long*>(&s_red), (unsigned long long)mine);
-    __syncthreads();
+    const long long tot = (nh == 2) ? P.hop_tot[c] : hop_phase1(G, P, c, nh - 2, n_rows, sm);
+    if (threadIdx.x == 0) P.hop_off[c] = draw_base;
+    const long long next_draws = light_hop(G, P, c, nh - 2, draw_base, rem0, next0, n_rows, G.fan[nh - 1], sm);
+    draw_base += tot >> 32;
     if (threadIdx.x == 0) P.last_off[c] = draw_base;
-    draw_base += s_red;
-    __syncthreads();
+    draw_base += next_draws;
   }
   // generator state after `draw_base` draws (torch's mt19937: `left` counts down from 624, reload when it hits 0)
   const long long T = draw_base;
@@ -359,13 +674,20 @@ sample_serial_kernel(Geom G, Ptrs P, int n_class, const int32_t* __restrict__ ba
     P.mt->left = (int32_t)left;
     P.mt->next = (int32_t)next;
     P.step_info[0] = T;
+#ifdef GS_DS_PROFILE
+    P.dbg[8] += clock64() - t_begin;
+#endif
   }
 }
 
 // ------------------------------------------------------------------------------------------ last hop, 1 CTA / class
-// transposed class block: rows = class-local columns, entries in source-row order (what a stable sort by column gives)
+// transposed class block: rows = class-local columns, entries in source-row order (what a stable sort by column gives).
+// Placement is inherently ordered, so ONE warp places 32 entries per step (__match_any_sync ranks equal columns, the
+// column cursors live in shared memory); the other warps stage the next 1024 entries into shared memory meanwhile, so a
+// step costs shared-memory latency only.
+constexpr int kTile = 1024;
 __device__ void build_transpose(const Geom& G, const Ptrs& P, int c, int h, int n_rows, int n_cols, int32_t* cursor_sm,
-                                long long* sm) {
+                                int32_t* tile_sm, long long* sm) {
   const int32_t* rowoff = P.rowoff[h] + (int64_t)c * (G.lcap[h] + 1);
   const int32_t* ocol = P.ocol[h] + (int64_t)c * G.ncap[h];
   const float* oval = P.oval[h] + (int64_t)c * G.ncap[h];
@@ -386,32 +708,58 @@ __device__ void build_transpose(const Geom& G, const Ptrs& P, int c, int h, int 
   for (int j = threadIdx.x; j < n_cols; j += blockDim.x) tr[j] = cursor[j];
   if (threadIdx.x == 0) tr[n_cols] = nnz;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    for (int e0 = 0; e0 < nnz; e0 += 32) {
-      const int e = e0 + lane;
-      const bool live = e < nnz;
-      const int cj = live ? ocol[e] : -1 - lane;
-      const unsigned m = __match_any_sync(0xffffffffu, cj);
-      const int rank = __popc(m & ((1u << lane) - 1u));
-      int base = 0;
-      if (live) base = cursor[cj];
-      __syncwarp();
-      if (live && rank == 0) cursor[cj] = base + __popc(m);
-      __syncwarp();
-      if (live) {
-        tc[base + rank] = erow[e];
-        tv[base + rank] = oval[e];
+  const int ntiles = (nnz + kTile - 1) / kTile;
+  auto stage = [&](int tl, int first_thread) {
+    int32_t* bc = tile_sm + (tl & 1) * 3 * kTile;
+    int32_t* br = bc + kTile;
+    float* bv = reinterpret_cast<float*>(br + kTile);
+    for (int i = threadIdx.x - first_thread; i < kTile; i += blockDim.x - first_thread) {
+      const int e = tl * kTile + i;
+      if (e < nnz) {
+        bc[i] = ocol[e];
+        br[i] = erow[e];
+        bv[i] = oval[e];
       }
     }
-  }
+  };
+  if (ntiles > 0) stage(0, 0);
   __syncthreads();
+  for (int tl = 0; tl < ntiles; ++tl) {
+    if (threadIdx.x >= 32) {
+      if (tl + 1 < ntiles) stage(tl + 1, 32);
+    } else {
+      const int lane = threadIdx.x;
+      const int32_t* bc = tile_sm + (tl & 1) * 3 * kTile;
+      const int32_t* br = bc + kTile;
+      const float* bv = reinterpret_cast<const float*>(br + kTile);
+      const int m_tile = min(kTile, nnz - tl * kTile);
+      for (int i0 = 0; i0 < m_tile; i0 += 32) {
+        const int i = i0 + lane;
+        const bool live = i < m_tile;
+        const int cj = live ? bc[i] : -1 - lane;
+        const unsigned m = __match_any_sync(0xffffffffu, cj);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        int base = 0;
+        if (live) base = cursor[cj];
+        __syncwarp();
+        if (live && rank == 0) cursor[cj] = base + __popc(m);
+        __syncwarp();
+        if (live) {
+          tc[base + rank] = br[i];
+          tv[base + rank] = bv[i];
+        }
+      }
+    }
+    __syncthreads();
+  }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 sample_last_kernel(Geom G, Ptrs P, int n_class, const uint8_t* __restrict__ materialise) {
-  extern __shared__ int32_t cursor_sm[];
-  __shared__ long long sm[kWarps + 1];
+  extern __shared__ int32_t dyn_sm[];
+  int32_t* cursor_sm = dyn_sm;
+  int32_t* tile_sm = dyn_sm + kCursorSmemInts;
+  __shared__ long long sm[kWarps + 2];
   const int c = blockIdx.x;
   if (c >= n_class) return;
   const bool keep = materialise == nullptr || materialise[c] != 0;
@@ -419,43 +767,68 @@ sample_last_kernel(Geom G, Ptrs P, int n_class, const uint8_t* __restrict__ mate
   int32_t* nid = P.nid + (int64_t)c * G.lcap[G.nh];
   int32_t* pos = P.pos + (int64_t)c * G.n;
   int32_t* lc = P.level_count + (int64_t)c * (G.nh + 1);
-  int n_rows = lc[G.nh - 1];
+  const int nh = G.nh;
+  uint32_t* uset_sm = reinterpret_cast<uint32_t*>(dyn_sm);      // the cursor region is idle during the hops
+  int n_rows = lc[nh >= 2 ? nh - 2 : 0];
+  const int n_pos = n_rows;                                     // nodes whose pos entry is set on entry
   if (keep) {
     long long dr;
-    n_rows = do_hop(G, P, c, G.nh - 1, true, P.last_off[c], rem0, next0, n_rows, &dr, sm);
-    if (threadIdx.x == 0) lc[G.nh] = n_rows;
+    if (nh >= 2) {
+      n_rows = do_hop(G, P, c, nh - 2, true, true, P.hop_off[c], rem0, next0, n_rows, &dr, sm, uset_sm);
+      if (threadIdx.x == 0) lc[nh - 1] = n_rows;
+      __syncthreads();
+    }
+    n_rows = do_hop(G, P, c, nh - 1, true, false, P.last_off[c], rem0, next0, n_rows, &dr, sm, uset_sm);
+    if (threadIdx.x == 0) lc[nh] = n_rows;
     __syncthreads();
-    for (int h = 0; h < G.nh; ++h) build_transpose(G, P, c, h, lc[h], lc[h + 1], cursor_sm, sm);
+    for (int h = 0; h < nh; ++h) build_transpose(G, P, c, h, lc[h], lc[h + 1], cursor_sm, tile_sm, sm);
+    for (int t = threadIdx.x; t < n_rows; t += blockDim.x) pos[nid[t]] = -1;
+  } else {
+    if (nh >= 2) {                                              // clear the light hop's markers
+      const int32_t* rowoff = P.rowoff[nh - 2] + (int64_t)c * (G.lcap[nh - 2] + 1);
+      const int32_t* cand_u = P.cand_u[nh - 2] + (int64_t)c * G.ncap[nh - 2];
+      int32_t* firstq = P.firstq + (int64_t)c * G.n;
+      const int n_cand = rowoff[n_rows];
+      for (int q = threadIdx.x; q < n_cand; q += blockDim.x) firstq[cand_u[q]] = INT_MAX;
+    }
+    for (int t = threadIdx.x; t < n_pos; t += blockDim.x) pos[nid[t]] = -1;
   }
-  for (int t = threadIdx.x; t < n_rows; t += blockDim.x) pos[nid[t]] = -1;
 }
 
 // ------------------------------------------------------------------------------------------ packing
 // Same layout and `desc` table as gs_sampler_finish_step (host_sampler.cpp); offsets are byte offsets into `out`.
-__global__ void pack_offsets_kernel(Geom G, Ptrs P, int n_class, const uint8_t* __restrict__ materialise, int has_labels,
-                                    int64_t out_cap, int64_t* __restrict__ desc) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(kThreads)
+pack_offsets_kernel(Geom G, Ptrs P, int n_class, const uint8_t* __restrict__ materialise, int has_labels,
+                    int64_t out_cap, int64_t* __restrict__ desc) {
+  __shared__ long long sm[kWarps + 2];
   const int nh = G.nh, al = G.align;
-  for (int i = 0; i < 64; ++i) desc[i] = -1;
   for (int l = 0; l <= nh; ++l) {
     int32_t* s = P.seg + (int64_t)l * (n_class + 1);
-    s[0] = 0;
-    for (int c = 0; c < n_class; ++c) {
-      const bool keep = materialise == nullptr || materialise[c] != 0;
-      const int cnt = keep ? P.level_count[(int64_t)c * (nh + 1) + l] : 0;
-      s[c + 1] = s[c] + (cnt + al - 1) / al * al;
-    }
+    const long long tot = block_scan<long long>(
+        n_class,
+        [&](int c) {
+          const bool keep = materialise == nullptr || materialise[c] != 0;
+          const int cnt = keep ? P.level_count[(int64_t)c * (nh + 1) + l] : 0;
+          return (long long)((cnt + al - 1) / al * al);
+        },
+        [&](int c, long long pre, long long) { s[c] = (int32_t)pre; }, sm);
+    if (threadIdx.x == 0) s[n_class] = (int32_t)tot;
   }
   for (int h = 0; h < nh; ++h) {
     int64_t* e = P.eoff + (int64_t)h * (n_class + 1);
-    e[0] = 0;
-    for (int c = 0; c < n_class; ++c) {
-      const bool keep = materialise == nullptr || materialise[c] != 0;
-      const int rows = P.level_count[(int64_t)c * (nh + 1) + h];
-      const int64_t m = keep ? (int64_t)(P.rowoff[h] + (int64_t)c * (G.lcap[h] + 1))[rows] : 0;
-      e[c + 1] = e[c] + m;
-    }
+    const long long tot = block_scan<long long>(
+        n_class,
+        [&](int c) {
+          const bool keep = materialise == nullptr || materialise[c] != 0;
+          const int rows = P.level_count[(int64_t)c * (nh + 1) + h];
+          return keep ? (long long)(P.rowoff[h] + (int64_t)c * (G.lcap[h] + 1))[rows] : 0ll;
+        },
+        [&](int c, long long pre, long long) { e[c] = pre; }, sm);
+    if (threadIdx.x == 0) e[n_class] = tot;
   }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int i = 0; i < 64; ++i) desc[i] = -1;
   int64_t off = 0;
   bool ok = true;
   auto reserve = [&](int64_t bytes) -> int64_t {
@@ -493,6 +866,7 @@ __global__ void pack_offsets_kernel(Geom G, Ptrs P, int n_class, const uint8_t* 
   desc[63] = ok ? 0 : GS_ENOSPC;
 }
 
+constexpr int kPackSplit = 8;    // CTAs per class in pack_copy_kernel (blockIdx.y)
 __global__ void __launch_bounds__(256)
 pack_copy_kernel(Geom G, Ptrs P, int n_class, const uint8_t* __restrict__ materialise, uint8_t* __restrict__ out,
                  const int64_t* __restrict__ desc) {
@@ -500,7 +874,7 @@ pack_copy_kernel(Geom G, Ptrs P, int n_class, const uint8_t* __restrict__ materi
   const int nh = G.nh;
   if (desc[63] != 0) return;
   const bool keep = materialise == nullptr || materialise[c] != 0;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x + blockDim.x * blockIdx.y, nt = blockDim.x * gridDim.y;
   const int32_t* lc = P.level_count + (int64_t)c * (nh + 1);
   int32_t* cnt = reinterpret_cast<int32_t*>(out + desc[14]);
   for (int l = tid; l <= nh; l += nt) cnt[(int64_t)l * n_class + c] = keep ? lc[l] : 0;
@@ -656,6 +1030,8 @@ gs_dsampler* gs_dsampler_create(int32_t n_nodes, const int32_t* d_rowptr, const 
   want((void**)&P.nid, nc * G.lcap[n_hops] * 4);
   want((void**)&P.level_count, nc * (n_hops + 1) * 4);
   want((void**)&P.last_off, nc * 8);
+  want((void**)&P.hop_off, nc * 8);
+  want((void**)&P.hop_tot, nc * 8);
   for (int h = 0; h < n_hops; ++h) {
     want((void**)&P.rowoff[h], nc * (G.lcap[h] + 1) * 4);
     want((void**)&P.drawoff[h], nc * G.lcap[h] * 4);
@@ -671,6 +1047,7 @@ gs_dsampler* gs_dsampler_create(int32_t n_nodes, const int32_t* d_rowptr, const 
   want((void**)&P.t_cursor, nc * G.lcap[n_hops] * 4);
   want((void**)&P.seg, (int64_t)(n_hops + 1) * (nc + 1) * 4);
   want((void**)&P.eoff, (int64_t)n_hops * (nc + 1) * 8);
+  want((void**)&P.dbg, 16 * 8);
   S->arena_bytes = off;
   cudaError_t e = cudaMalloc(&S->arena, (size_t)off);
   if (e != cudaSuccess) {
@@ -680,6 +1057,7 @@ gs_dsampler* gs_dsampler_create(int32_t n_nodes, const int32_t* d_rowptr, const 
   }
   for (const Piece& p : pieces) *p.dst = static_cast<uint8_t*>(S->arena) + p.at;
   cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(P.dbg, 0, 16 * 8, st);
   fill_i32_kernel<<<kNumSMs * 4, 256, 0, st>>>(P.pos, nc * (int64_t)n_nodes, -1);
   finish_launch("dsampler_fill_pos");
   fill_i32_kernel<<<kNumSMs * 4, 256, 0, st>>>(P.firstq, nc * (int64_t)n_nodes, INT_MAX);
@@ -698,7 +1076,15 @@ gs_dsampler* gs_dsampler_create(int32_t n_nodes, const int32_t* d_rowptr, const 
     cap += 4 * lvl + 4 * 4 * rows0 + 4 * (int64_t)(n_hops + 1) * nc + 16 * 8;
     S->out_cap = cap;
   }
-  if (cudaFuncSetAttribute(sample_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCursorSmemInts * 4) !=
+  if (cudaFuncSetAttribute(sample_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           USetSm::kWords * kThreads * 4) != cudaSuccess) {
+    cudaGetLastError();
+    set_error_msg("gs_dsampler_create: cannot reserve shared memory for the serial sampling kernel");
+    cudaFree(S->arena);
+    delete S;
+    return nullptr;
+  }
+  if (cudaFuncSetAttribute(sample_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCursorSmemInts + 2 * 3 * kTile) * 4) !=
       cudaSuccess) {
     cudaGetLastError();
     set_error_msg("gs_dsampler_create: cannot reserve shared memory for the transposed-block cursors");
@@ -769,13 +1155,15 @@ int gs_dsampler_sample_step(gs_dsampler* S, int32_t n_class, const int32_t* d_ba
   mt_generate_kernel<<<1, 256, 0, st>>>(S->P.mt, S->P.R, (int)nblocks, S->P.step_info);
   int rc = finish_launch("dsampler_mt_generate");
   if (rc) return rc;
-  sample_serial_kernel<<<1, kThreads, 0, st>>>(G, S->P, n_class, d_batch, d_batch_off, d_materialise);
+  sample_prep_kernel<<<n_class, kThreads, 0, st>>>(G, S->P, n_class, d_batch, d_batch_off);
+  if ((rc = finish_launch("dsampler_prep"))) return rc;
+  sample_serial_kernel<<<1, kThreads, USetSm::kWords * kThreads * 4, st>>>(G, S->P, n_class, d_materialise);
   if ((rc = finish_launch("dsampler_serial"))) return rc;
-  sample_last_kernel<<<n_class, kThreads, kCursorSmemInts * 4, st>>>(G, S->P, n_class, d_materialise);
+  sample_last_kernel<<<n_class, kThreads, (kCursorSmemInts + 2 * 3 * kTile) * 4, st>>>(G, S->P, n_class, d_materialise);
   if ((rc = finish_launch("dsampler_last_hop"))) return rc;
-  pack_offsets_kernel<<<1, 32, 0, st>>>(G, S->P, n_class, d_materialise, S->has_labels ? 1 : 0, out_cap, d_desc);
+  pack_offsets_kernel<<<1, kThreads, 0, st>>>(G, S->P, n_class, d_materialise, S->has_labels ? 1 : 0, out_cap, d_desc);
   if ((rc = finish_launch("dsampler_pack_offsets"))) return rc;
-  pack_copy_kernel<<<n_class, 256, 0, st>>>(G, S->P, n_class, d_materialise, d_out, d_desc);
+  pack_copy_kernel<<<dim3(n_class, kPackSplit), 256, 0, st>>>(G, S->P, n_class, d_materialise, d_out, d_desc);
   return finish_launch("dsampler_pack_copy");
 }
 
@@ -794,3 +1182,11 @@ int64_t gs_uset_emul_order(const int64_t* keys, int64_t n, int64_t* out) {
 }
 
 }  // extern "C"
+
+extern "C" int gs_dsampler_debug_counters(gs_dsampler* S, int64_t* out16, void* stream) {
+  GS_REQUIRE(S && out16);
+  cudaStream_t st = gs::as_stream(stream);
+  cudaError_t e = cudaMemcpyAsync(out16, S->P.dbg, 16 * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e == cudaSuccess ? GS_OK : (int)e;
+}

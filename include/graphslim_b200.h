@@ -254,6 +254,8 @@ int gs_dsampler_get_rng(gs_dsampler* s, uint32_t* state, int32_t* left, int32_t*
 int gs_dsampler_sample_step(gs_dsampler* s, int32_t n_class, const int32_t* d_batch, const int32_t* d_batch_off,
                             const uint8_t* d_materialise, int32_t max_batch, uint8_t* d_out, int64_t out_cap,
                             int64_t* d_desc, void* stream);
+/* phase cycle counters of the serial sampling kernel (all zero unless the library was built with -DGS_DS_PROFILE) */
+int gs_dsampler_debug_counters(gs_dsampler* s, int64_t* out16 /* host */, void* stream);
 /* host-side check of the std::unordered_set iteration-order restatement used by the device sampler (tests) */
 int64_t gs_uset_emul_order(const int64_t* keys, int64_t n, int64_t* out);
 

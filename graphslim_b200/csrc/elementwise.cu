@@ -216,33 +216,51 @@ __global__ void match_apply_kernel(int rows, int cols, const float* __restrict__
 }
 
 // ---------------------------------------------------------------- per-class column sums (bias gradients)
-// out[out_block[g]*cols + c] = sum_{r in seg[g]..seg[g+1]} X[r, c]; blockIdx.y = group, a block owns 32 columns and
-// splits the segment's rows over its 8 warps.
-__global__ void segment_colsum_kernel(const int32_t* __restrict__ seg, const int32_t* __restrict__ out_block, int cols,
-                                      const float* __restrict__ X, int64_t ldx, float* __restrict__ out) {
-  __shared__ float sm[8][32];
-  const int g = blockIdx.y;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int w = threadIdx.x >> 5;
-  const int r0 = seg[g], r1 = seg[g + 1];
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  if (c < cols) {
-    int r = r0 + w;
-    for (; r + 24 < r1; r += 32) {
-      a0 += X[(int64_t)r * ldx + c];
-      a1 += X[(int64_t)(r + 8) * ldx + c];
-      a2 += X[(int64_t)(r + 16) * ldx + c];
-      a3 += X[(int64_t)(r + 24) * ldx + c];
-    }
-    for (; r < r1; r += 8) a0 += X[(int64_t)r * ldx + c];
+// out[out_block[g]*cols + c] += sum_{r in seg[g]..seg[g+1]} X[r, c]   (out zeroed by the caller).
+// The row range seg[0]..seg[G] is cut into 64-row runs, one per warp (blockIdx.y * 8 + warp), a lane per column of the
+// block's 32-column tile; a run keeps eight row loads in flight, follows the segment boundaries it crosses and commits
+// one atomic per (segment, column).  Parallelism comes from the rows, not from the number of groups.
+constexpr int kColsumRun = 64;
+__global__ void __launch_bounds__(256)
+segment_colsum_kernel(int G, const int32_t* __restrict__ seg, const int32_t* __restrict__ out_block, int cols,
+                      const float* __restrict__ X, int64_t ldx, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool live = c < cols;
+  const int r_last = __ldg(seg + G);
+  int r = __ldg(seg) + (blockIdx.y * 8 + w) * kColsumRun;
+  const int r_end = min(r + kColsumRun, r_last);
+  if (r >= r_end) return;
+  int lo = 0, hi = G - 1;                 // last g with seg[g] <= r: the non-empty segment that holds row r
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(seg + mid) <= r) lo = mid;
+    else hi = mid - 1;
   }
-  sm[w][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
-  __syncthreads();
-  if (w == 0 && c < cols) {
-    float v = 0.f;
+  int g = lo;
+  const float* x = X + c;
+  while (r < r_end) {
+    const int s_end = min(r_end, __ldg(seg + g + 1));
+    float a[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v += sm[i][threadIdx.x];
-    out[(int64_t)out_block[g] * cols + c] = v;
+    for (int i = 0; i < 8; ++i) a[i] = 0.f;
+    if (live) {
+      for (; r + 8 <= s_end; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(x + (int64_t)(r + i) * ldx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] += v[i];
+      }
+      for (; r < s_end; ++r) a[0] += __ldg(x + (int64_t)r * ldx);
+      const float sum = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+      atomicAdd(out + (int64_t)__ldg(out_block + g) * cols + c, sum);
+    }
+    r = s_end;
+    if (r < r_end) {
+      ++g;
+      while (__ldg(seg + g + 1) <= r) ++g;   // skip empty segments
+    }
   }
 }
 
@@ -407,11 +425,11 @@ int gs_match_apply_f32(int32_t rows, int32_t cols, const float* gs_, const float
 }
 
 int gs_segment_colsum_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t cols, const float* X,
-                          int64_t ldx, float* out, void* stream) {
-  GS_REQUIRE(G >= 0 && seg && out_block && cols >= 0 && X && out && ldx >= cols);
-  if (G == 0 || cols == 0) return GS_OK;
-  dim3 grid((cols + 31) / 32, G);
-  segment_colsum_kernel<<<grid, 256, 0, as_stream(stream)>>>(seg, out_block, cols, X, ldx, out);
+                          int64_t ldx, int32_t n_rows, float* out, void* stream) {
+  GS_REQUIRE(G >= 0 && seg && out_block && cols >= 0 && X && out && ldx >= cols && n_rows >= 0);
+  if (G == 0 || cols == 0 || n_rows == 0) return GS_OK;
+  dim3 grid((cols + 31) / 32, (n_rows + 8 * kColsumRun - 1) / (8 * kColsumRun));
+  segment_colsum_kernel<<<grid, 256, 0, as_stream(stream)>>>(G, seg, out_block, cols, X, ldx, out);
   return finish_launch("segment_colsum");
 }
 

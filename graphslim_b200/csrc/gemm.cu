@@ -13,7 +13,8 @@ namespace gs {
 
 int gemm_tc_dispatch(int ta, int tb, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B,
                      int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* workspace,
-                     int64_t workspace_bytes, cudaStream_t st);
+                     int64_t workspace_bytes, const float* bias, int relu, const float* mask, int64_t ldmask,
+                     cudaStream_t st);
 int64_t gemm_tc_workspace_bytes(int M, int N, int K, int precision);
 int gemm_tc_grouped_dispatch(int G, const int32_t* seg, const int32_t* out_block, int M, int N, int K_total,
                              const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
@@ -35,6 +36,11 @@ struct GemmProblem {
   // output column block out_block[g]
   const int32_t* seg;
   const int32_t* out_block;
+  // fused epilogue (splits == 1, not grouped): v += bias[col]; relu; v = mask[row,col] > 0 ? v : 0
+  const float* bias;
+  int relu;
+  const float* mask;
+  int64_t ldmask;
 };
 
 template <int BM, int BN, int BK, int TM, int TN>
@@ -128,10 +134,12 @@ gemm_simt_kernel(GemmProblem p) {
       const float v = p.alpha * acc[i][j];
       if (atomic) {
         atomicAdd(c, v);
-      } else if (p.beta == 0.f) {
-        *c = v;
       } else {
-        *c = fmaf(p.beta, *c, v);
+        float o = (p.beta == 0.f) ? v : fmaf(p.beta, *c, v);
+        if (p.bias) o += __ldg(p.bias + gn);
+        if (p.relu) o = fmaxf(o, 0.f);
+        if (p.mask) o = __ldg(p.mask + (int64_t)gm * p.ldmask + gn) > 0.f ? o : 0.f;
+        *c = o;
       }
     }
   }
@@ -160,25 +168,29 @@ static int launch_simt(GemmProblem& p, int gz, cudaStream_t st) {
 
 extern "C" {
 
-int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
-                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* workspace,
-                int64_t workspace_bytes, void* stream) {
+int gs_gemm_epi_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
+                    const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int relu,
+                    const float* mask, int64_t ldmask, int precision, void* workspace, int64_t workspace_bytes,
+                    void* stream) {
   GS_REQUIRE(M >= 0 && N >= 0 && K >= 0 && C && ldc >= N);
   GS_REQUIRE(K == 0 || (A && B));
   GS_REQUIRE(K == 0 || lda >= (ta ? M : K));
   GS_REQUIRE(K == 0 || ldb >= (tb ? K : N));
+  GS_REQUIRE(!mask || ldmask >= N);
   if (M == 0 || N == 0) return GS_OK;
+  const bool epi = bias || relu || mask;
   cudaStream_t st = gs::as_stream(stream);
   if (precision != 0) {
     const int rc = gs::gemm_tc_dispatch(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, precision, workspace,
-                                        workspace_bytes, st);
+                                        workspace_bytes, bias, relu, mask, ldmask, st);
     if (rc != GS_ENOSYS) return rc;  // GS_ENOSYS: shape not covered by the tensor-core kernels
   }
-  gs::GemmProblem p{ta, tb, M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, 1, K, nullptr, nullptr};
-  // split K when the output alone cannot fill the machine (e.g. dW = dY^T H with K = N'^2)
+  gs::GemmProblem p{ta, tb, M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, 1, K, nullptr, nullptr, bias, relu, mask, ldmask};
+  // split K when the output alone cannot fill the machine (e.g. dW = dY^T H with K = N'^2); a fused epilogue needs
+  // the complete sum in one thread, so those products stay unsplit
   const int64_t tiles = (int64_t)((M + 63) / 64) * ((N + 63) / 64);
   int splits = 1;
-  if (K >= 2048 && tiles < 2 * gs::kNumSMs) {
+  if (K >= 2048 && tiles < 2 * gs::kNumSMs && !epi) {
     splits = (int)((2 * gs::kNumSMs + tiles - 1) / tiles);
     const int max_splits = (K + 511) / 512;
     if (splits > max_splits) splits = max_splits;
@@ -200,6 +212,13 @@ int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, co
   return gs::launch_simt(p, p.splits, st);
 }
 
+int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
+                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* workspace,
+                int64_t workspace_bytes, void* stream) {
+  return gs_gemm_epi_f32(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nullptr, 0, nullptr, 0, precision,
+                         workspace, workspace_bytes, stream);
+}
+
 int64_t gs_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K, int precision) {
   return gs::gemm_tc_workspace_bytes(M, N, K, precision);
 }
@@ -214,7 +233,7 @@ int gs_gemm_grouped_tn_f32(int32_t G, const int32_t* seg, const int32_t* out_blo
                                                 workspace, workspace_bytes, gs::as_stream(stream));
     if (rc != GS_ENOSYS) return rc;
   }
-  gs::GemmProblem p{1, 0, M, N, 0, 1.f, 0.f, A, lda, B, ldb, C, ldc, 1, 0, seg, out_block};
+  gs::GemmProblem p{1, 0, M, N, 0, 1.f, 0.f, A, lda, B, ldb, C, ldc, 1, 0, seg, out_block, nullptr, 0, nullptr, 0};
   return gs::launch_simt(p, G, gs::as_stream(stream));
 }
 

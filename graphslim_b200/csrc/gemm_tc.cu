@@ -32,6 +32,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -66,6 +67,11 @@ struct Params {
   const int32_t* seg;
   const int32_t* out_block;
   int groups;
+  // fused epilogue (never with split-K / grouped accumulation): v += bias[col]; relu; v = mask[row,col] > 0 ? v : 0
+  const float* bias;
+  int relu;
+  const float* mask;
+  int64_t ldmask;
 };
 
 struct Tile {
@@ -543,7 +549,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
         __syncwarp();
         const int c4 = (lane & 7) * 4, rsub = lane >> 3;
         if (vec_c) {
-          float* cbase = p.C + (int64_t)(row_base + rsub) * p.ldc + tl.c_col + nb * BN + c0 + c4;
+          const int gcol = nb * BN + c0 + c4;
+          float* cbase = p.C + (int64_t)(row_base + rsub) * p.ldc + tl.c_col + gcol;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) {
+            const float* bp = p.bias + gcol;
+            if ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) bv = __ldg(reinterpret_cast<const float4*>(bp));
+            else bv = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+          }
+          const bool vec_m = p.mask && ((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 v = *reinterpret_cast<const float4*>(st + (rsub + 4 * i) * 36 + c4);
@@ -557,6 +571,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
                 v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y);
                 v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
               }
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              if (p.relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
+              if (p.mask) {
+                const float* mp = p.mask + (int64_t)(row_base + rsub + 4 * i) * p.ldmask + gcol;
+                float4 m;
+                if (vec_m) m = __ldg(reinterpret_cast<const float4*>(mp));
+                else m = make_float4(__ldg(mp), __ldg(mp + 1), __ldg(mp + 2), __ldg(mp + 3));
+                v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+                v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+              }
               *reinterpret_cast<float4*>(c) = v;
             }
           }
@@ -569,13 +595,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
               const int gc = nb * BN + c0 + c4 + e;
               if (gc >= p.N) break;
               float* c = p.C + (int64_t)row * p.ldc + tl.c_col + gc;
-              const float v = p.alpha * st[(rsub + 4 * i) * 36 + c4 + e];
+              float v = p.alpha * st[(rsub + 4 * i) * 36 + c4 + e];
               if (use_atomics) {
                 atomicAdd(c, v);
-              } else if (p.beta == 0.f) {
-                *c = v;
               } else {
-                *c = fmaf(p.beta, *c, v);
+                if (p.beta != 0.f) v = fmaf(p.beta, *c, v);
+                if (p.bias) v += __ldg(p.bias + gc);
+                if (p.relu) v = fmaxf(v, 0.f);
+                if (p.mask) v = __ldg(p.mask + (int64_t)row * p.ldmask + gc) > 0.f ? v : 0.f;
+                *c = v;
               }
             }
           }
@@ -600,6 +628,23 @@ __global__ void scale_matrix_tc_kernel(int M, int N, float* C, int64_t ldc, floa
   if (i >= (int64_t)M * N) return;
   float* c = C + (i / N) * ldc + (i % N);
   *c = (beta == 0.f) ? 0.f : *c * beta;
+}
+
+// Tuning knobs for small products (read once): GS_TC_MIN_KB = fewest 64-wide k-blocks a K split may be left with
+// (default 2), GS_TC_SHRINK_BN = 1 lets small problems use narrower accumulator tiles so that more CTAs share them.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static int tune_min_kb() {
+  static int v = -1;
+  if (v < 0) v = std::max(1, env_int("GS_TC_MIN_KB", 2));
+  return v;
+}
+static int tune_shrink_bn() {
+  static int v = -1;
+  if (v < 0) v = env_int("GS_TC_SHRINK_BN", 1);
+  return v;
 }
 
 template <int BN, int NPASS>
@@ -661,9 +706,10 @@ static int launch(Params& p, void* workspace, int64_t workspace_bytes, cudaStrea
   } else {
     // split K when the output tiles alone cannot occupy the SMs
     int splits = 1;
-    if (mn_tiles < kNumSMs && kblocks >= 8) {
+    const int min_kb = tune_min_kb();
+    if (mn_tiles < kNumSMs && kblocks >= 2 * min_kb && !p.bias && !p.relu && !p.mask) {
       splits = (int)((kNumSMs + mn_tiles - 1) / mn_tiles);
-      if (splits > kblocks / 4) splits = kblocks / 4;
+      if (splits > kblocks / min_kb) splits = kblocks / min_kb;
       if (splits < 1) splits = 1;
     }
     int kchunk = ((kblocks + splits - 1) / splits) * BK;
@@ -687,7 +733,17 @@ static int launch(Params& p, void* workspace, int64_t workspace_bytes, cudaStrea
 
 // Called by gs_gemm_f32 when precision != 0.  Returns GS_ENOSYS for shapes better served by the SIMT path
 // (tiny products where a 128-row tile would be mostly padding).
-static inline int tc_bn(int N) { return N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32)); }
+static inline int tc_bn_wide(int N) { return N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32)); }
+// accumulator width: the widest tile that does not waste more than half of its columns -- narrowed for small problems
+// until the output tiles cover about half of the SMs (a 909 x 256 product is 8 tiles at BN = 256 but 64 at BN = 32;
+// the A conversion repeated per column tile is negligible at that size, the serial epilogue per CTA is not)
+static inline int tc_bn(int M, int N) {
+  int bn = tc_bn_wide(N);
+  if (!tc::tune_shrink_bn()) return bn;
+  const int64_t tm = (M + tc::BM - 1) / tc::BM;
+  while (bn > 32 && tm * ((N + bn - 1) / bn) < kNumSMs / 2 && (N + bn / 2 - 1) / (bn / 2) > (N + bn - 1) / bn) bn >>= 1;
+  return bn;
+}
 
 bool gemm_tc_covers(int M, int N, int K) {
   return !(K < 32 || N < 16 || (int64_t)M * N * K < (int64_t)1 << 22);
@@ -695,19 +751,20 @@ bool gemm_tc_covers(int M, int N, int K) {
 
 int64_t gemm_tc_workspace_bytes(int M, int N, int K, int precision) {
   if (precision == 0 || !gemm_tc_covers(M, N, K)) return 0;
-  const int bn = tc_bn(N);
+  const int bn = tc_bn_wide(N);      // upper bound over the tile widths tc_bn(M, N) may pick (same image size for all)
   const int64_t planes = precision == 1 ? 2 : 1;
   return (int64_t)((N + bn - 1) / bn) * ((K + tc::BK - 1) / tc::BK) * planes * bn * tc::BK * 2;
 }
 
 int gemm_tc_dispatch(int ta, int tb, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B,
                      int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* workspace,
-                     int64_t workspace_bytes, cudaStream_t st) {
+                     int64_t workspace_bytes, const float* bias, int relu, const float* mask, int64_t ldmask,
+                     cudaStream_t st) {
   if (!gemm_tc_covers(M, N, K)) return GS_ENOSYS;
-  tc::Params p{ta, tb, M, N, K, alpha, beta, A, lda, B, ldb, nullptr, C, ldc, 1, K, 0, 0, nullptr, nullptr, 0};
+  tc::Params p{ta, tb, M, N, K, alpha, beta, A, lda, B, ldb, nullptr, C, ldc, 1, K, 0, 0, nullptr, nullptr, 0,
+               bias, relu, mask, ldmask};
   const bool three = precision == 1;
-  // accumulator width: the widest tile that does not waste more than half of its columns
-  switch (tc_bn(N)) {
+  switch (tc_bn(M, N)) {
     case 256:
       return three ? tc::launch<256, 3>(p, workspace, workspace_bytes, st) : tc::launch<256, 1>(p, workspace, workspace_bytes, st);
     case 128:
@@ -726,9 +783,10 @@ int gemm_tc_grouped_dispatch(int G, const int32_t* seg, const int32_t* out_block
                              const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                              int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
   if (!gemm_tc_covers(M, N, K_total) || M < 8) return GS_ENOSYS;
-  tc::Params p{1, 0, M, N, K_total, 1.f, 0.f, A, lda, B, ldb, nullptr, C, ldc, 1, K_total, 0, 0, seg, out_block, G};
+  tc::Params p{1, 0, M, N, K_total, 1.f, 0.f, A, lda, B, ldb, nullptr, C, ldc, 1, K_total, 0, 0, seg, out_block, G,
+               nullptr, 0, nullptr, 0};
   const bool three = precision == 1;
-  switch (tc_bn(N)) {
+  switch (tc_bn_wide(N)) {
     case 256:
       return three ? tc::launch<256, 3>(p, workspace, workspace_bytes, st) : tc::launch<256, 1>(p, workspace, workspace_bytes, st);
     case 128:

@@ -12,11 +12,14 @@
 //     gather is one fully coalesced 512 B * NV request per non-zero (rows are padded to 32 B);
 //   * narrow widths (F/4 < 32, e.g. the class-width propagations of SGC) split the warp into
 //     groups that take alternate non-zeros and are combined with warp shuffles.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gs {
 
 constexpr int kWarpsPerBlock = 8;
+constexpr int kWideWarpsPerBlock = 8;   // default of the wide kernel (see GS_SPMM_WPB)
 
 template <int VEC>
 struct V;
@@ -85,15 +88,15 @@ __device__ __forceinline__ bool item_range(const Items& it, int i, int& row, int
 }
 
 // Wide rows: L = ceil(F/VEC) >= 32 vector columns, tiled by 32*NV per warp (blockIdx.y = column tile).
-template <int VEC, int NV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int VEC, int NV, int WPB, int UNR>
+__global__ void __launch_bounds__(WPB * 32)
 spmm_wide_kernel(Items it, const int32_t* __restrict__ col, const float* __restrict__ val,
                  const float* __restrict__ X, int64_t ldx, int L, float* __restrict__ Y, int64_t ldy, int mode) {
   using VT = typename V<VEC>::T;
-  __shared__ int32_t s_col[kWarpsPerBlock][32];
-  __shared__ float s_val[kWarpsPerBlock][32];
+  __shared__ int32_t s_col[WPB][32];
+  __shared__ float s_val[WPB][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * kWarpsPerBlock + warp;
+  const int item = blockIdx.x * WPB + warp;
   if (item >= it.n_items) return;
   int row, beg, end;
   bool atomic;
@@ -115,7 +118,7 @@ spmm_wide_kernel(Items it, const int32_t* __restrict__ col, const float* __restr
       s_val[warp][lane] = __ldg(val + base + lane);
     }
     __syncwarp();
-#pragma unroll 4
+#pragma unroll UNR
     for (int j = 0; j < cnt; ++j) {
       const float a = s_val[warp][j];
       const float* xr = X + (int64_t)s_col[warp][j] * ldx + (int64_t)(tile0 + lane) * VEC;
@@ -191,10 +194,30 @@ static int launch_spmm(const Items& it, const int32_t* col, const float* val, co
   const int ntiles = (L + 255) / 256;
   const int per_tile = (L + ntiles - 1) / ntiles;
   const int nv = (per_tile + 31) / 32;
-  dim3 grid(gx, (L + 32 * nv - 1) / (32 * nv));
-#define GS_SPMM_CASE(NVV)                                                                                        \
-  case NVV:                                                                                                      \
-    spmm_wide_kernel<VEC, NVV><<<grid, kWarpsPerBlock * 32, 0, st>>>(it, col, val, X, ldx, L, Y, ldy, mode);     \
+  // GS_SPMM_WPB (8|4|2) and GS_SPMM_UNR (4|8): tuning knobs of the wide kernel, read once
+  static int wpb = 0, unr = 0;
+  if (wpb == 0) {
+    const char* e = getenv("GS_SPMM_WPB");
+    wpb = e ? atoi(e) : kWideWarpsPerBlock;
+    if (wpb != 8 && wpb != 4 && wpb != 2) wpb = kWideWarpsPerBlock;
+    const char* u = getenv("GS_SPMM_UNR");
+    unr = (u && atoi(u) == 8) ? 8 : 4;
+  }
+  const int gxw = (it.n_items + wpb - 1) / wpb;
+  dim3 grid(gxw, (L + 32 * nv - 1) / (32 * nv));
+#define GS_SPMM_LAUNCH(NVV, W, U) \
+  spmm_wide_kernel<VEC, NVV, W, U><<<grid, W * 32, 0, st>>>(it, col, val, X, ldx, L, Y, ldy, mode)
+#define GS_SPMM_CASE(NVV)                                              \
+  case NVV:                                                            \
+    if (unr == 8) {                                                    \
+      if (wpb == 8) GS_SPMM_LAUNCH(NVV, 8, 8);                         \
+      else if (wpb == 4) GS_SPMM_LAUNCH(NVV, 4, 8);                    \
+      else GS_SPMM_LAUNCH(NVV, 2, 8);                                  \
+    } else {                                                           \
+      if (wpb == 8) GS_SPMM_LAUNCH(NVV, 8, 4);                         \
+      else if (wpb == 4) GS_SPMM_LAUNCH(NVV, 4, 4);                    \
+      else GS_SPMM_LAUNCH(NVV, 2, 4);                                  \
+    }                                                                  \
     break;
   switch (nv) {
     GS_SPMM_CASE(1)
@@ -209,6 +232,7 @@ static int launch_spmm(const Items& it, const int32_t* col, const float* val, co
       return GS_EINVAL;
   }
 #undef GS_SPMM_CASE
+#undef GS_SPMM_LAUNCH
   return finish_launch("spmm_wide");
 }
 

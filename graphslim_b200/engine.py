@@ -56,10 +56,13 @@ class _ModelBase:
         self.W = None
 
     # propagate with the dense synthetic adjacency (or identity for GCondX)
-    def _prop(self, A, M, transpose=False, fresh=False):
+    def _prop(self, A, M, transpose=False, fresh=False, bias=None, relu=False):
+        """A M (or A^T M), optionally followed by + bias and ReLU inside the product's store."""
         if self.identity_adj:
-            return M.clone() if fresh else M          # `fresh`: the caller will modify the result in place
-        return self.K.gemm(A, M, ta=transpose)
+            epi = bias is not None or relu
+            out = M.clone() if (fresh or epi) else M  # `fresh`: the caller will modify the result in place
+            return self.K.bias_act(out, bias, relu=relu) if epi else out
+        return self.K.gemm(A, M, ta=transpose, bias=bias, relu=relu)
 
     def set_weights(self, W):
         self.W = W
@@ -163,8 +166,8 @@ class SGC2(_ModelBase):
         K = self.K
         W1, b1, W2, b2 = self.W
         Xg = K.gather_rows(X_full, rb.nid)
-        H1 = K.bias_act(K.gemm(Xg, W1), b1, relu=True)
-        U = K.bias_act(K.gemm(H1, W2), b2, relu=False)
+        H1 = K.gemm(Xg, W1, bias=b1, relu=True)
+        U = K.gemm(H1, W2, bias=b2)
         T = U
         for blk in rb.blocks_fwd:
             T = K.spmm(blk.csr, T)
@@ -175,7 +178,7 @@ class SGC2(_ModelBase):
         seg, ids, nb = rb.seg[-1], rb.out_block, self.lay.nblk
         gW2 = K.gemm_grouped_tn(H1, dU, seg, ids, nb, aligned=rb.aligned)
         gb2 = K.segment_colsum(dU, seg, ids, nb)
-        dA1 = K.relu_mask(K.gemm(dU, W2, tb=True), H1)
+        dA1 = K.gemm(dU, W2, tb=True, mask=H1)
         gW1 = K.gemm_grouped_tn(Xg, dA1, seg, ids, nb, aligned=rb.aligned)
         gb1 = K.segment_colsum(dA1, seg, ids, nb)
         return [gW1, gb1, gW2, gb2]
@@ -184,8 +187,8 @@ class SGC2(_ModelBase):
         K = self.K
         W1, b1, W2, b2 = self.W
         self.X, self.A = X, A
-        self.H1 = K.bias_act(K.gemm(X, W1), b1, relu=True)
-        U = K.bias_act(K.gemm(self.H1, W2), b2, relu=False)
+        self.H1 = K.gemm(X, W1, bias=b1, relu=True)
+        U = K.gemm(self.H1, W2, bias=b2)
         self.Tz = [U]
         for _ in range(self.k):
             self.Tz.append(self._prop(A, self.Tz[-1]))
@@ -256,7 +259,7 @@ class SGC2(_ModelBase):
         ones = _ones_col(K, X.shape[0])
         gW2 = K.gemm(self.H1, dU, ta=True)
         gb2 = K.colsum(dU).view(-1)
-        dA1 = K.relu_mask(K.gemm(dU, W2, tb=True), self.H1)
+        dA1 = K.gemm(dU, W2, tb=True, mask=self.H1)
         gW1 = K.gemm(X, dA1, ta=True)
         gb1 = K.colsum(dA1).view(-1)
         return [gW1, gb1, gW2, gb2]
@@ -275,7 +278,7 @@ class GCN2(_ModelBase):
         outer, inner = rb.blocks_fwd
         Xp = X_full if X_padded is None else X_padded
         T2 = K.spmm(outer.with_global_cols(), Xp)[:, :X_full.shape[1]]   # (A2 X[n_id]) W1 == A2 (X[n_id] W1)
-        H1 = K.bias_act(K.gemm(T2, W1), b1, relu=True)
+        H1 = K.gemm(T2, W1, bias=b1, relu=True)
         M2 = K.gemm(H1, W2)
         Z = K.bias_act(K.spmm(inner.csr, M2), b2, relu=False)
         _, R = K.softmax_residual(Z, rb.labels, rb.inv_b)
@@ -284,7 +287,7 @@ class GCN2(_ModelBase):
         dM2 = K.spmm(inner.csr_t, R)
         seg1 = rb.seg[1]
         gW2 = K.gemm_grouped_tn(H1, dM2, seg1, ids, nb, aligned=rb.aligned)
-        dA1 = K.relu_mask(K.gemm(dM2, W2, tb=True), H1)
+        dA1 = K.gemm(dM2, W2, tb=True, mask=H1)
         gb1 = K.segment_colsum(dA1, seg1, ids, nb)
         gW1 = K.gemm_grouped_tn(T2, dA1, seg1, ids, nb, aligned=rb.aligned)
         return [gW1, gb1, gW2, gb2]
@@ -294,9 +297,9 @@ class GCN2(_ModelBase):
         W1, b1, W2, b2 = self.W
         self.X, self.A = X, A
         self.M1 = K.gemm(X, W1)
-        self.H1 = K.bias_act(self._prop(A, self.M1, fresh=True), b1, relu=True)
+        self.H1 = self._prop(A, self.M1, bias=b1, relu=True)
         self.M2 = K.gemm(self.H1, W2)
-        self.Z = K.bias_act(self._prop(A, self.M2, fresh=True), b2, relu=False)
+        self.Z = self._prop(A, self.M2, bias=b2)
         return self.Z
 
     def syn_grads(self):
@@ -357,7 +360,7 @@ class GCN2(_ModelBase):
         gb2 = K.colsum(R).view(-1)
         dM2 = self._prop(A, R, transpose=True)
         gW2 = K.gemm(self.H1, dM2, ta=True)
-        dA1 = K.relu_mask(K.gemm(dM2, W2, tb=True), self.H1)
+        dA1 = K.gemm(dM2, W2, tb=True, mask=self.H1)
         gb1 = K.colsum(dA1).view(-1)
         dM1 = self._prop(A, dA1, transpose=True)
         gW1 = K.gemm(X, dM1, ta=True)

@@ -104,7 +104,10 @@ class CudaOps:
         return _Timed(self, tag)
 
     # -- dense ---------------------------------------------------------------------------------
-    def gemm(self, A, B, ta=False, tb=False, out=None, alpha=1.0, beta=0.0, precision=None):
+    def gemm(self, A, B, ta=False, tb=False, out=None, alpha=1.0, beta=0.0, precision=None, bias=None, relu=False,
+             mask=None):
+        """out = epi(alpha op(A) op(B) + beta out); epi adds `bias` per column, applies ReLU, and zeroes the entries
+        whose `mask` (same shape as out) is not positive -- all inside the product's store."""
         lda, ldb = _mat(A, "A"), _mat(B, "B")
         M, K = (A.shape[1], A.shape[0]) if ta else (A.shape[0], A.shape[1])
         K2, N = (B.shape[1], B.shape[0]) if tb else (B.shape[0], B.shape[1])
@@ -123,8 +126,22 @@ class CudaOps:
             ws_bytes = int(self.lib.gs_gemm_workspace_bytes(M, N, K, prec))
             if ws_bytes:
                 ws = self._gemm_workspace(ws_bytes)
-        _lib.check(self.lib.gs_gemm_f32(int(ta), int(tb), M, N, K, alpha, _ptr(A), lda, _ptr(B), ldb, beta,
-                                        _ptr(out), ldc, prec, _ptr(ws), ws_bytes, self.stream), "gs_gemm_f32")
+        if bias is None and mask is None and not relu:
+            _lib.check(self.lib.gs_gemm_f32(int(ta), int(tb), M, N, K, alpha, _ptr(A), lda, _ptr(B), ldb, beta,
+                                            _ptr(out), ldc, prec, _ptr(ws), ws_bytes, self.stream), "gs_gemm_f32")
+            return out
+        ldm = 0
+        if mask is not None:
+            ldm = _mat(mask, "mask")
+            if mask.shape != (M, N):
+                raise ValueError(f"gemm mask shape {tuple(mask.shape)} != {(M, N)}")
+        if bias is not None:
+            _f32(bias, "bias")
+            if bias.numel() != N or not bias.is_contiguous():
+                raise ValueError("gemm bias must be a contiguous vector of N elements")
+        _lib.check(self.lib.gs_gemm_epi_f32(int(ta), int(tb), M, N, K, alpha, _ptr(A), lda, _ptr(B), ldb, beta,
+                                            _ptr(out), ldc, _ptr(bias), int(bool(relu)), _ptr(mask), ldm, prec,
+                                            _ptr(ws), ws_bytes, self.stream), "gs_gemm_epi_f32")
         return out
 
     def _gemm_workspace(self, nbytes):
@@ -159,9 +176,9 @@ class CudaOps:
         ldx = _mat(X, "X")
         cols = X.shape[1]
         G = seg.numel() - 1
-        out = self.zeros(1, nblk * cols) if G < nblk else self.empty(1, nblk * cols)
-        _lib.check(self.lib.gs_segment_colsum_f32(G, _ptr(seg), _ptr(out_block), cols, _ptr(X), ldx, _ptr(out),
-                                                  self.stream), "gs_segment_colsum_f32")
+        out = self.zeros(1, nblk * cols)
+        _lib.check(self.lib.gs_segment_colsum_f32(G, _ptr(seg), _ptr(out_block), cols, _ptr(X), ldx, X.shape[0],
+                                                  _ptr(out), self.stream), "gs_segment_colsum_f32")
         return out
 
     def colsum(self, X):

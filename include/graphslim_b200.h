@@ -79,6 +79,16 @@ int gs_gemm_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, co
                 const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int precision, void* workspace,
                 int64_t workspace_bytes, void* stream);
 
+/* The same product with the element-wise tail of the layer fused into the store:
+ *   C = epi(alpha * op(A) * op(B) + beta * C),  epi(v)[r,c] = mask ? (mask[r,c] > 0 ? w : 0) : w,
+ *   w = relu ? max(v + bias[c], 0) : v + bias[c]        (bias / mask may be NULL)
+ * i.e. `x @ W + b` followed by ReLU (models/layers.py:377-381, models/sgc.py:39-41) and, in the backward, the ReLU
+ * mask of the saved activation.  The product is never K-split, so each output element is finished by one thread. */
+int gs_gemm_epi_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
+                    const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int relu,
+                    const float* mask, int64_t ldmask, int precision, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
 /* Grouped K-segmented product for per-class weight gradients:
  * C[:, out_block[g]*N : (out_block[g]+1)*N] = A[seg[g]:seg[g+1], :M]^T * B[seg[g]:seg[g+1], :N]
  * (autograd.grad w.r.t. layer weights, one class per group; condensation/gcond_base.py:223,234).
@@ -89,10 +99,11 @@ int gs_gemm_grouped_tn_f32(int32_t G, const int32_t* seg, const int32_t* out_blo
                            int32_t K_total, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                            int64_t ldc, int precision, void* workspace, int64_t workspace_bytes, void* stream);
 
-/* out[out_block[g]*cols + c] = sum over rows seg[g]..seg[g+1] of X[r, c]  (per-class bias gradients); blocks of
- * groups that are not listed are left untouched */
+/* out[out_block[g]*cols + c] += sum over rows seg[g]..seg[g+1] of X[r, c]  (per-class bias gradients,
+ * autograd.grad w.r.t. the biases at condensation/gcond_base.py:223,234).  seg is non-decreasing, n_rows >= seg[G]
+ * bounds the row range (rows of X); `out` is zero-initialised by the caller and accumulated with atomics. */
 int gs_segment_colsum_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t cols, const float* X,
-                          int64_t ldx, float* out, void* stream);
+                          int64_t ldx, int32_t n_rows, float* out, void* stream);
 
 /* ---- small fused kernels of the condense model ------------------------------------------- */
 /* Z[r,c] += bias[c]; optional ReLU (models/layers.py:48-51,378-381; models/sgc.py:41) */

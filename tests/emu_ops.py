@@ -32,16 +32,22 @@ class EmuOps:
         return contextlib.nullcontext()
 
     # ---- dense
-    def gemm(self, A, B, ta=False, tb=False, out=None, alpha=1.0, beta=0.0, precision=None):
+    def gemm(self, A, B, ta=False, tb=False, out=None, alpha=1.0, beta=0.0, precision=None, bias=None, relu=False,
+             mask=None):
         a = A.T if ta else A
         b = B.T if tb else B
         r = alpha * (a @ b)
+        if out is not None and beta != 0.0:
+            r = out * beta + r
+        if bias is not None:
+            r = r + bias
+        if relu:
+            r = r.clamp(min=0)
+        if mask is not None:
+            r = r * (mask > 0).to(r.dtype)
         if out is None:
             return r
-        if beta == 0.0:
-            out.copy_(r)
-        else:
-            out.mul_(beta).add_(r)
+        out.copy_(r)
         return out
 
     def gemm_grouped_tn(self, A, B, seg, out_block, nblk, aligned=False, precision=None):

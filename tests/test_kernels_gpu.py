@@ -89,6 +89,42 @@ def test_spmm_long_rows_chunked(K, E):
     close(got, ref)
 
 
+def _spmm_seq_fp32(csr, X):
+    """Row by row, non-zeros in CSR order, one fused multiply-add per element: the order gs_spmm_csr_f32 promises.
+    float64 fma emulation is exact for fp32 products, so rounding once per step reproduces fmaf."""
+    rp, col, val = csr.rowptr.numpy(), csr.col.numpy(), csr.val.numpy().astype(np.float64)
+    Xd = X.numpy().astype(np.float64)
+    out = np.zeros((csr.n_rows, X.shape[1]), dtype=np.float32)
+    for r in range(csr.n_rows):
+        acc = np.zeros(X.shape[1], dtype=np.float32)
+        for e in range(rp[r], rp[r + 1]):
+            acc = (val[e] * Xd[col[e]] + acc.astype(np.float64)).astype(np.float32)
+        out[r] = acc
+    return torch.from_numpy(out)
+
+
+@pytest.mark.parametrize("n_rows", [1, 7, 40000])
+def test_spmm_row_order_bit_exact(K, n_rows):
+    """Rows of 0..200 non-zeros (multi-slice rows, empty rows, slices of exactly 32): the result equals the sequential
+    CSR-order fp32 fused-multiply-add accumulation bit for bit."""
+    gen = np.random.default_rng(n_rows)
+    n_cols = 3000
+    deg = gen.choice([0, 1, 2, 5, 31, 32, 33, 64, 65, 200], n_rows, p=[.1, .2, .2, .2, .05, .05, .05, .05, .05, .05])
+    rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum(deg)
+    col = gen.integers(0, n_cols, rowptr[-1])
+    val = gen.standard_normal(col.size).astype(np.float32)
+    csr = Csr(torch.from_numpy(rowptr.astype(np.int32)), torch.from_numpy(col.astype(np.int32)), torch.from_numpy(val),
+              n_rows, n_cols)
+    X = torch.from_numpy(gen.standard_normal((n_cols, 128)).astype(np.float32))
+    got = K.spmm(to_dev(csr, "cuda"), X.cuda()).cpu()
+    sub = slice(0, min(n_rows, 600))
+    ref = _spmm_seq_fp32(Csr(csr.rowptr[: sub.stop + 1], csr.col, csr.val, sub.stop, n_cols), X)
+    assert torch.equal(got[sub], ref)
+    tail = Csr(csr.rowptr[-201:] if n_rows > 200 else csr.rowptr, csr.col, csr.val, min(n_rows, 200), n_cols)
+    assert torch.equal(got[-tail.n_rows:], _spmm_seq_fp32(tail, X))
+
+
 def test_spmm_transpose_and_scatter_agree(K, E):
     gen = np.random.default_rng(7)
     csr = rand_csr(400, 650, 6, gen)

@@ -56,6 +56,18 @@ def powerlaw_csr(n, nnz_target, seed, dev):
     return rowptr.to(torch.int32), col.to(torch.int32), val
 
 
+VARIANTS = {
+    "v1_smem_row_per_warp": (1, 4, 0, 0),
+    "v2_default": (2, 0, 0, 3),
+    "v2_unr4": (2, 4, 0, 3),
+    "v2_unr8": (2, 8, 0, 3),
+    "v2_group1": (2, 0, 1, 3),
+    "v2_group4": (2, 0, 4, 3),
+    "v2_group16": (2, 0, 16, 3),
+    "v2_nohints": (2, 0, 0, 0),
+}
+
+
 def time_it(fn, flush, iters=8):
     ts = []
     for i in range(iters + 2):
@@ -73,6 +85,7 @@ def time_it(fn, flush, iters=8):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--variants", action="store_true", help="also time every tuning of the wide kernel (VARIANTS)")
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_spmm_sweep.json"))
     ns = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -83,7 +96,7 @@ def main():
     grid = [(10**5, 8), (10**6, 8), (10**6, 64), (10**7, 8), (10**7, 64), (10**8, 64), (10**8, 492)]
     feats = [128, 256, 500, 602]
     if ns.quick:
-        grid, feats = [(10**6, 8), (10**7, 64)], [128, 602]
+        grid, feats = [(10**6, 8), (10**7, 8), (10**7, 64), (10**8, 492)], [128, 602]
     rows = []
     for nnz_t, avg in grid:
         n = max(1000, nnz_t // avg)
@@ -101,6 +114,20 @@ def main():
             outp = torch.zeros(n, ld, device=dev)
             out = outp[:, :F]
             # rows are padded to 32 B with zeros, so the kernel runs at the padded width (float4 for any F)
+            variants = {}
+            if ns.variants:
+                # (impl, unr, rows per warp, cache-hint flags) of gs_spmm_set_tuning; every variant must give the same bits
+                base = None
+                for name, tune in VARIANTS.items():
+                    K.spmm_set_tuning(*tune)
+                    outp.zero_()
+                    variants[name] = time_it(lambda: K.spmm(csr, Xp, out=outp), flush, iters=5)
+                    if base is None:
+                        base = outp.clone()
+                    elif not torch.equal(base, outp):
+                        variants[name + "_MISMATCH"] = float((base - outp).abs().max())
+                del base
+                K.spmm_set_tuning()
             ms = time_it(lambda: K.spmm(csr, Xp, out=outp), flush)
             ref = torch.sparse.mm(tcsr, X.contiguous())
             err = float((out - ref).abs().max() / ref.abs().max())
@@ -111,6 +138,8 @@ def main():
             rec = dict(nnz=nnz, n=n, avg_deg=avg, max_deg=max_deg, F=F, ms=ms, alg_GBps=alg / ms / 1e6,
                        alg_frac_of_hbm=alg / ms / 1e6 / peak, gather_GBps=gather / ms / 1e6,
                        x_MB=4 * F * n / 1e6, torch_sparse_csr_mm_ms=ms_t, speedup_vs_torch_csr=ms_t / ms, max_rel_err=err)
+            if variants:
+                rec["variants_ms"] = variants
             rows.append(rec)
             print(json.dumps(rec), flush=True)
             del Xp, out, ref, Xc

@@ -12,6 +12,16 @@
 //     gather is one fully coalesced 512 B * NV request per non-zero (rows are padded to 32 B);
 //   * narrow widths (F/4 < 32, e.g. the class-width propagations of SGC) split the warp into
 //     groups that take alternate non-zeros and are combined with warp shuffles.
+//
+// Two generations of the wide kernel live here (gs_spmm_set_tuning picks one; both produce the same bits:
+// one accumulator per output element, non-zeros in CSR order, one fmaf per non-zero):
+//   v1  one work item per warp, (col,val) staged through shared memory;
+//   v2  a warp owns R consecutive work items and software-pipelines them: the item descriptors are fetched
+//       with one coalesced load, the next 32 (col,val) pairs are always in flight in registers (across row
+//       boundaries) while the current ones are consumed, and the feature-row gathers are issued UNR at a
+//       time before their FMAs, so a warp keeps UNR*NV 512-byte requests outstanding instead of stalling
+//       on the rowptr -> col -> X dependent chain once per row.  Outputs are written with streaming stores
+//       and (col,val) are read evict-first so the gathered rows of X keep the L2.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -30,6 +40,7 @@ struct V<4> {
   static __device__ __forceinline__ T ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
   static __device__ __forceinline__ T ldrw(const float* p) { return *reinterpret_cast<const float4*>(p); }
   static __device__ __forceinline__ void st(float* p, T v) { *reinterpret_cast<float4*>(p) = v; }
+  static __device__ __forceinline__ void stcs(float* p, T v) { __stcs(reinterpret_cast<float4*>(p), v); }
   static __device__ __forceinline__ void fma(T& a, float s, T x) {
     a.x = fmaf(s, x.x, a.x);
     a.y = fmaf(s, x.y, a.y);
@@ -52,6 +63,7 @@ struct V<1> {
   static __device__ __forceinline__ T ld(const float* p) { return __ldg(p); }
   static __device__ __forceinline__ T ldrw(const float* p) { return *p; }
   static __device__ __forceinline__ void st(float* p, T v) { *p = v; }
+  static __device__ __forceinline__ void stcs(float* p, T v) { __stcs(p, v); }
   static __device__ __forceinline__ void fma(T& a, float s, T x) { a = fmaf(s, x, a); }
   static __device__ __forceinline__ T add(T a, T b) { return a + b; }
   static __device__ __forceinline__ T shfl_xor(T a, int o) { return __shfl_xor_sync(0xffffffffu, a, o); }
@@ -179,6 +191,173 @@ spmm_narrow_kernel(Items it, const int32_t* __restrict__ col, const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2: pipelined multi-item warps (see the header comment).
+struct Tuning {
+  int impl;    // 1 | 2
+  int unr;     // 0 = by width, else 2 | 4 | 8
+  int group;   // 0 = by problem size, else items per warp (1..32)
+  int flags;   // bit0: streaming stores of Y, bit1: evict-first loads of (col,val)
+};
+static Tuning g_tune = {2, 0, 0, 3};
+
+constexpr int kV2Warps = 4;   // small CTAs: the register-heavy instantiations still fill an SM in 4-warp steps
+
+template <int VEC, int NV, int UNR>
+__global__ void __launch_bounds__(kV2Warps * 32)
+spmm_wide_v2_kernel(Items it, const int32_t* __restrict__ col, const float* __restrict__ val,
+                    const float* __restrict__ X, int64_t ldx, int L, float* __restrict__ Y, int64_t ldy, int mode0,
+                    int R, int flags) {
+  using VT = typename V<VEC>::T;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * kV2Warps + (threadIdx.x >> 5);
+  const int64_t g0 = wid * R;
+  if (g0 >= it.n_items) return;
+  const int nseg = (int)min((int64_t)R, (int64_t)it.n_items - g0);
+  const bool cs_store = flags & 1, cs_load = flags & 2;
+
+  // lane i holds the descriptor of the warp's i-th item
+  int s_row = 0, s_beg = 0, s_end = 0;
+  bool s_atomic = false, s_valid = false;
+  if (lane < nseg) s_valid = item_range(it, (int)(g0 + lane), s_row, s_beg, s_end, s_atomic);
+  if (!s_valid) s_end = s_beg;
+
+  const int tile0 = blockIdx.y * (32 * NV);
+  bool live[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) live[v] = (tile0 + v * 32 + lane) < L;
+  const int64_t lane_off = (int64_t)(tile0 + lane) * VEC;
+
+  auto load_pair = [&](int base, int end, int& c, float& a) {
+    c = 0;
+    a = 0.f;
+    if (base + lane < end) {
+      if (cs_load) {
+        c = __ldcs(col + base + lane);
+        a = __ldcs(val + base + lane);
+      } else {
+        c = __ldg(col + base + lane);
+        a = __ldg(val + base + lane);
+      }
+    }
+  };
+
+  // cursor: item ci, 32-slice [cbase, min(cbase+32, cend)), its (col,val) in (c, a)
+  int ci = 0;
+  int cbase = __shfl_sync(FULL, s_beg, 0), cend = __shfl_sync(FULL, s_end, 0);
+  int c;
+  float a;
+  load_pair(cbase, cend, c, a);
+  VT acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = V<VEC>::zero();
+
+  while (ci < nseg) {
+    // where the next slice is (same item, or the head of the next item) -- and put its loads in flight
+    const bool last_slice = cbase + 32 >= cend;
+    int ni = ci, nbase = cbase + 32, nend = cend;
+    if (last_slice) {
+      ni = ci + 1;
+      const int src = min(ni, 31);
+      nbase = __shfl_sync(FULL, s_beg, src);
+      nend = __shfl_sync(FULL, s_end, src);
+      if (ni >= nseg) nend = nbase;
+    }
+    int c2;
+    float a2;
+    load_pair(nbase, nend, c2, a2);
+
+    const int cnt = min(32, cend - cbase);
+    for (int j = 0; j < cnt; j += UNR) {
+      VT x[UNR][NV];
+      float aj[UNR];
+#pragma unroll
+      for (int k = 0; k < UNR; ++k) {
+        const int src = min(j + k, 31);
+        const int cj = __shfl_sync(FULL, c, src);
+        aj[k] = __shfl_sync(FULL, a, src);
+        const float* xr = X + (int64_t)cj * ldx + lane_off;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          x[k][v] = V<VEC>::zero();
+          if (j + k < cnt && live[v]) x[k][v] = V<VEC>::ld(xr + (int64_t)v * 32 * VEC);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < UNR; ++k) {
+        if (j + k < cnt) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) V<VEC>::fma(acc[v], aj[k], x[k][v]);
+        }
+      }
+    }
+
+    if (last_slice) {
+      const bool valid = __shfl_sync(FULL, (int)s_valid, ci) != 0;
+      const bool atomic = __shfl_sync(FULL, (int)s_atomic, ci) != 0;
+      const int row = __shfl_sync(FULL, s_row, ci);
+      if (valid) {
+        const int mode = atomic ? 2 : mode0;
+        float* yr = Y + (int64_t)row * ldy + lane_off;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (!live[v]) continue;
+          float* p = yr + (int64_t)v * 32 * VEC;
+          if (mode == 2) {
+            V<VEC>::atomic_add(p, acc[v]);
+          } else if (mode == 1) {
+            V<VEC>::st(p, V<VEC>::add(V<VEC>::ldrw(p), acc[v]));
+          } else if (cs_store) {
+            V<VEC>::stcs(p, acc[v]);
+          } else {
+            V<VEC>::st(p, acc[v]);
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] = V<VEC>::zero();
+    }
+    ci = ni;
+    cbase = nbase;
+    cend = nend;
+    c = c2;
+    a = a2;
+  }
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = kNumSMs;
+  }
+  return n;
+}
+
+template <int VEC, int NV>
+static void launch_wide_v2(const Items& it, const int32_t* col, const float* val, const float* X, int64_t ldx, int L,
+                           float* Y, int64_t ldy, int mode, int n_tiles, cudaStream_t st) {
+  // items per warp: enough warps for >= 4 waves of 32 resident warps per SM, at most 8 items (16 for huge inputs)
+  int R = g_tune.group;
+  if (R <= 0) {
+    const int64_t warps_wanted = (int64_t)sm_count() * 32 * 4;
+    R = (int)min((int64_t)8, max((int64_t)1, (int64_t)it.n_items / warps_wanted));
+  }
+  R = max(1, min(R, 32));
+  const int64_t n_warps = ((int64_t)it.n_items + R - 1) / R;
+  dim3 grid((unsigned)((n_warps + kV2Warps - 1) / kV2Warps), n_tiles);
+  int unr = g_tune.unr > 0 ? g_tune.unr : (NV <= 2 ? 8 : 4);
+  if (NV * unr > 24) unr = NV * 4 > 24 ? 2 : 4;          // keep the in-flight tile within the register file
+#define GS_V2(U) spmm_wide_v2_kernel<VEC, NV, U><<<grid, kV2Warps * 32, 0, st>>>(it, col, val, X, ldx, L, Y, ldy, mode, R, g_tune.flags)
+  if (unr >= 8) GS_V2(8);
+  else if (unr >= 4) GS_V2(4);
+  else GS_V2(2);
+#undef GS_V2
+}
+
 template <int VEC>
 static int launch_spmm(const Items& it, const int32_t* col, const float* val, const float* X, int64_t ldx, int F,
                        float* Y, int64_t ldy, int mode, cudaStream_t st) {
@@ -194,6 +373,17 @@ static int launch_spmm(const Items& it, const int32_t* col, const float* val, co
   const int ntiles = (L + 255) / 256;
   const int per_tile = (L + ntiles - 1) / ntiles;
   const int nv = (per_tile + 31) / 32;
+  if (g_tune.impl == 2) {
+    const int n_tiles = (L + 32 * nv - 1) / (32 * nv);
+    switch (nv) {
+#define GS_V2_CASE(NVV) case NVV: launch_wide_v2<VEC, NVV>(it, col, val, X, ldx, L, Y, ldy, mode, n_tiles, st); break;
+      GS_V2_CASE(1) GS_V2_CASE(2) GS_V2_CASE(3) GS_V2_CASE(4) GS_V2_CASE(5) GS_V2_CASE(6) GS_V2_CASE(7) GS_V2_CASE(8)
+#undef GS_V2_CASE
+      default:
+        return GS_EINVAL;
+    }
+    return finish_launch("spmm_wide_v2");
+  }
   // GS_SPMM_WPB (8|4|2) and GS_SPMM_UNR (4|8): tuning knobs of the wide kernel, read once
   static int wpb = 0, unr = 0;
   if (wpb == 0) {
@@ -325,6 +515,13 @@ int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, c
   }
   if (v4) return gs::launch_spmm<4>(it, col, val, X, ldx, F, Y, ldy, mode, st);
   return gs::launch_spmm<1>(it, col, val, X, ldx, F, Y, ldy, mode, st);
+}
+
+int gs_spmm_set_tuning(int impl, int unr, int group, int flags) {
+  GS_REQUIRE((impl == 1 || impl == 2) && (unr == 0 || unr == 2 || unr == 4 || unr == 8) && group >= 0 && group <= 32 &&
+             flags >= 0 && flags <= 3);
+  gs::g_tune = gs::Tuning{impl, unr, group, flags};
+  return GS_OK;
 }
 
 int gs_spmm_csr_scatter_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val,

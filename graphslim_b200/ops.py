@@ -209,6 +209,10 @@ class CudaOps:
                                             _ptr(cb), _ptr(ce), self.stream), "gs_spmm_csr_f32")
         return out
 
+    def spmm_set_tuning(self, impl=2, unr=0, group=0, flags=3):
+        """Kernel generation / in-flight gathers / rows per warp / cache hints of the wide SpMM (include/graphslim_b200.h)."""
+        _lib.check(self.lib.gs_spmm_set_tuning(int(impl), int(unr), int(group), int(flags)), "gs_spmm_set_tuning")
+
     def spmm_scatter(self, csr, dY, out):
         """out[col[e],:] += val[e]*dY[row(e),:] (atomics); `out` must be pre-initialised."""
         ldy, ldx = _mat(dY, "dY"), _mat(out, "out")

@@ -52,6 +52,14 @@ int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, c
                     int32_t n_chunks, int32_t long_thr, const int32_t* chunk_row, const int32_t* chunk_beg,
                     const int32_t* chunk_end, void* stream);
 
+/* Tuning of the wide (F >= 128) SpMM kernel; process-wide, not thread-safe against concurrent launches.
+ *   impl  1 = one row per warp, (col,val) staged in shared memory; 2 = pipelined multi-row warps (default)
+ *   unr   feature-row gathers in flight per warp (0 = chosen from the width, else 2|4|8)
+ *   group work items per warp for impl 2 (0 = chosen from the problem size, else 1..32)
+ *   flags bit0 streaming stores of Y, bit1 evict-first loads of (col,val)   (default 3)
+ * Every setting produces the same bits (CSR-order fmaf accumulation); no reference counterpart. */
+int gs_spmm_set_tuning(int impl, int unr, int group, int flags);
+
 /* Transpose-free backward through a rectangular block: dX[col[e],:] += val[e] * dY[r,:] (atomics).
  * autograd of torch_sparse.matmul inside torch.autograd.grad at condensation/gcond_base.py:223. */
 int gs_spmm_csr_scatter_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val,

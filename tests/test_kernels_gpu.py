@@ -125,6 +125,45 @@ def test_spmm_row_order_bit_exact(K, n_rows):
     assert torch.equal(got[-tail.n_rows:], _spmm_seq_fp32(tail, X))
 
 
+@pytest.mark.parametrize("F", [128, 130, 256, 384, 608, 1024, 1436])
+def test_spmm_tunings_bit_identical(K, F):
+    """Every gs_spmm_set_tuning setting (kernel generation, gathers in flight, rows per warp, cache hints) promises the
+    same bits: CSR-order fmaf accumulation for whole rows; rows sliced for atomics are compared with a tolerance."""
+    from graphslim_b200.graph_utils import build_row_chunks, chunks_to_device
+    gen = np.random.default_rng(F)
+    n_rows, n_cols = 5000, 4000
+    deg = gen.choice([0, 1, 2, 5, 31, 32, 33, 64, 65, 97, 300], n_rows, p=[.1, .2, .2, .2, .05, .05, .05, .05, .04, .03, .03])
+    rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum(deg)
+    col = gen.integers(0, n_cols, rowptr[-1])
+    val = gen.standard_normal(col.size).astype(np.float32)
+    csr = to_dev(Csr(torch.from_numpy(rowptr.astype(np.int32)), torch.from_numpy(col.astype(np.int32)),
+                     torch.from_numpy(val), n_rows, n_cols), "cuda")
+    X = torch.from_numpy(gen.standard_normal((n_cols, F)).astype(np.float32)).cuda()
+    base0 = torch.from_numpy(gen.standard_normal((n_rows, F)).astype(np.float32)).cuda()
+    tunings = [(1, 4, 0, 0), (2, 0, 0, 3), (2, 2, 0, 3), (2, 4, 1, 0), (2, 8, 3, 1), (2, 0, 16, 2), (2, 4, 32, 3)]
+    try:
+        outs = []
+        for t in tunings:
+            K.spmm_set_tuning(*t)
+            plain = K.spmm(csr, X)
+            acc = K.spmm(csr, X, out=base0.clone(), accumulate=True)
+            csr.chunks = chunks_to_device(build_row_chunks(rowptr, 64), "cuda")
+            sliced = K.spmm(csr, X)
+            csr.chunks = None
+            outs.append((plain, acc, sliced))
+        for plain, acc, sliced in outs[1:]:
+            assert torch.equal(plain, outs[0][0])
+            assert torch.equal(acc, outs[0][1])
+            short = torch.from_numpy(deg <= 64).cuda()
+            assert torch.equal(sliced[short], outs[0][0][short])
+            close(sliced.cpu(), outs[0][0].cpu())
+        sub = Csr(csr.rowptr[:301].cpu(), csr.col.cpu(), csr.val.cpu(), 300, n_cols)
+        assert torch.equal(outs[1][0][:300].cpu(), _spmm_seq_fp32(sub, X.cpu()))
+    finally:
+        K.spmm_set_tuning()
+
+
 def test_spmm_transpose_and_scatter_agree(K, E):
     gen = np.random.default_rng(7)
     csr = rand_csr(400, 650, 6, gen)

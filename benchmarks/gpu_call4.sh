@@ -2,6 +2,12 @@
 # round 1, session 4: parity tests, SpMM tuning sweep, arxiv + Reddit bench, launch list, ncu full of the SpMM (one GPU)
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt
+# the new SpMM generation first, in its own process: if it is broken the rest of the call runs on the v1 kernel
+if timeout 300 python -m pytest tests/test_kernels_gpu.py -q -k "spmm" > gpurun_out/pytest_spmm.log 2>&1; then
+  echo "spmm tests green (v2)"
+else
+  echo "spmm tests FAILED on v2 -> GS_SPMM_IMPL=1 for the rest"; tail -30 gpurun_out/pytest_spmm.log; export GS_SPMM_IMPL=1
+fi
 ( time timeout 1000 python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log

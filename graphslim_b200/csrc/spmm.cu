@@ -199,7 +199,13 @@ struct Tuning {
   int group;   // 0 = by problem size, else items per warp (1..32)
   int flags;   // bit0: streaming stores of Y, bit1: evict-first loads of (col,val)
 };
-static Tuning g_tune = {2, 0, 0, 3};
+static Tuning env_tuning() {
+  Tuning t{2, 0, 0, 3};
+  const char* e = getenv("GS_SPMM_IMPL");     // escape hatch for A/B runs: 1 selects the v1 kernel process-wide
+  if (e && atoi(e) == 1) t = Tuning{1, 4, 0, 0};
+  return t;
+}
+static Tuning g_tune = env_tuning();
 
 constexpr int kV2Warps = 4;   // small CTAs: the register-heavy instantiations still fill an SM in 4-warp steps
 

@@ -339,7 +339,8 @@ class DeviceClassSampler(_Unpack):
     start of an epoch, advanced there by the sampling kernels, and written back when the epoch ends, so both streams
     are consumed exactly as the reference consumes them."""
 
-    RING = 3
+    RING = 4            # blocks of steps i (being consumed), i+1, i+2 (sampling ahead) + the slot being recycled
+    DEPTH = 2           # steps sampled ahead of the consumer: collect() then never waits for the side stream
 
     def __init__(self, adj_csr, members, dataset, nlayers, device, labels=None, batch=256, align=64):
         """adj_csr: ops.Csr of the normalised graph in HBM (int32 rowptr/col, fp32 val); labels: int32 device tensor."""
@@ -360,7 +361,8 @@ class DeviceClassSampler(_Unpack):
         self.align = int(align)
         self.labels = None if labels is None else labels.to(self.device, torch.int32).contiguous()
         self.max_batch = int(min(batch, max(len(m) for m in self.members)))
-        self.side = torch.cuda.Stream(self.device)
+        # high priority: the sampler's short serial kernels are scheduled ahead of the main stream's wide ones
+        self.side = torch.cuda.Stream(self.device, priority=-1)
         with torch.cuda.device(self.device):
             self.handle = self.lib.gs_dsampler_create(
                 self.n, adj_csr.rowptr.data_ptr(), adj_csr.col.data_ptr(), adj_csr.val.data_ptr(),
@@ -490,7 +492,7 @@ class DeviceClassSampler(_Unpack):
 
 
 class _DevicePrefetcher:
-    """Sampling of step i+1 runs on the side stream while step i is consumed.  A worker thread draws the class
+    """Sampling of steps i+1 .. i+DEPTH runs on the side stream while step i is consumed.  A worker thread draws the class
     batches (numpy releases the GIL inside the shuffle); the kernels are queued from the consumer's thread."""
 
     def __init__(self, sampler, n_steps, materialise):
@@ -503,8 +505,8 @@ class _DevicePrefetcher:
         self.i = 0
         self.prev_slot = None
         self.slots = {}
-        if n_steps > 0:
-            self._launch(0)
+        for k in range(min(self.s.DEPTH, n_steps)):
+            self._launch(k)
 
     def _draw(self):
         try:
@@ -533,8 +535,8 @@ class _DevicePrefetcher:
         i = self.i
         if self.prev_slot is not None:
             self.s.release(self.prev_slot)       # everything that read step i-1's blocks is queued by now
-        if i + 1 < self.n:
-            self._launch(i + 1)
+        if i + self.s.DEPTH < self.n:
+            self._launch(i + self.s.DEPTH)
         slot = self.slots.pop(i)
         rb = self.s.collect(slot, self.mat)
         self.prev_slot = slot

@@ -33,11 +33,11 @@ def main():
     seen = collections.Counter()
     orig = K.gemm
 
-    def spy(A, B, ta=False, tb=False, out=None, alpha=1.0, beta=0.0, precision=None):
+    def spy(A, B, ta=False, tb=False, out=None, alpha=1.0, beta=0.0, precision=None, **epi):
         M, Kk = (A.shape[1], A.shape[0]) if ta else (A.shape[0], A.shape[1])
         N = B.shape[0] if tb else B.shape[1]
         seen[(int(ta), int(tb), M, N, Kk, float(beta) != 0.0)] += 1
-        return orig(A, B, ta, tb, out, alpha, beta, precision)
+        return orig(A, B, ta, tb, out, alpha, beta, precision, **epi)
 
     K.gemm = spy
     agent.run_epoch(0)

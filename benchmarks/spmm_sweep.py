@@ -56,15 +56,23 @@ def powerlaw_csr(n, nnz_target, seed, dev):
     return rowptr.to(torch.int32), col.to(torch.int32), val
 
 
-VARIANTS = {
-    "v1_smem_row_per_warp": (1, 4, 0, 0),
-    "v2_default": (2, 0, 0, 3),
-    "v2_unr4": (2, 4, 0, 3),
-    "v2_unr8": (2, 8, 0, 3),
-    "v2_group1": (2, 0, 1, 3),
-    "v2_group4": (2, 0, 4, 3),
-    "v2_group16": (2, 0, 16, 3),
-    "v2_nohints": (2, 0, 0, 0),
+VARIANTS = {   # gs_spmm_set_tuning(impl, unr, group, flags, wpb, max_nv)
+    "v1": (1, 4, 0, 0, 8, 8),
+    "v1_unr8": (1, 8, 0, 0, 8, 8),
+    "v1_wpb4": (1, 4, 0, 0, 4, 8),
+    "v1_wpb2": (1, 4, 0, 0, 2, 8),
+    "v1_wpb4_unr8": (1, 8, 0, 0, 4, 8),
+    "v1_cs": (1, 4, 0, 3, 8, 8),
+    "v1_l2pf": (1, 4, 0, 4, 8, 8),
+    "v1_l2pf_unr8": (1, 8, 0, 4, 8, 8),
+    "v1_l2pf_cs_store": (1, 4, 0, 5, 8, 8),
+    "v1_nv4": (1, 4, 0, 0, 8, 4),
+    "v1_nv2": (1, 4, 0, 0, 8, 2),
+    "v1_nv1": (1, 4, 0, 0, 8, 1),
+    "v1_nv1_l2pf": (1, 4, 0, 4, 8, 1),
+    "v1_nv2_l2pf_unr8": (1, 8, 0, 4, 8, 2),
+    "v2": (2, 0, 0, 3, 8, 8),
+    "v2_group1": (2, 0, 1, 3, 8, 8),
 }
 
 
@@ -86,6 +94,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--variants", action="store_true", help="also time every tuning of the wide kernel (VARIANTS)")
+    ap.add_argument("--long-row", type=int, default=512, help="rows with more non-zeros are sliced (atomics)")
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_spmm_sweep.json"))
     ns = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -102,7 +111,7 @@ def main():
         n = max(1000, nnz_t // avg)
         rowptr, col, val = powerlaw_csr(n, nnz_t, seed=nnz_t % 97 + avg, dev=dev)
         nnz = col.numel()
-        chunks = chunks_to_device(build_row_chunks(rowptr.cpu().numpy(), 512), dev)
+        chunks = chunks_to_device(build_row_chunks(rowptr.cpu().numpy(), ns.long_row), dev)
         csr = Csr(rowptr, col, val, n, n, chunks)
         max_deg = int((rowptr[1:] - rowptr[:-1]).max())
         tcsr = torch.sparse_csr_tensor(rowptr.long(), col.long(), val, size=(n, n))
@@ -145,7 +154,7 @@ def main():
             del Xp, out, ref, Xc
         del tcsr, csr
         torch.cuda.empty_cache()
-    json.dump(dict(hbm_peak_GBps=peak, note="torch.sparse CSR mm is a stand-in for the reference's torch_sparse path",
+    json.dump(dict(hbm_peak_GBps=peak, long_row_nnz=ns.long_row, note="torch.sparse CSR mm is a stand-in for the reference's torch_sparse path",
                    rows=rows), open(ns.out, "w"), indent=1)
 
 

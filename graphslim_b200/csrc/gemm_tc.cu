@@ -67,7 +67,12 @@ struct Params {
   const int32_t* seg;
   const int32_t* out_block;
   int groups;
-  // fused epilogue (never with split-K / grouped accumulation): v += bias[col]; relu; v = mask[row,col] > 0 ? v : 0
+};
+
+// fused epilogue (never with split-K / grouped accumulation): v += bias[col]; relu; v = mask[row,col] > 0 ? v : 0.
+// A separate kernel parameter: growing `Params` itself changes ptxas' register allocation of the producer loop (8 ->
+// 24 bytes of spills and a 25 % slower streaming product were measured when these fields lived in Params).
+struct Epi {
   const float* bias;
   int relu;
   const float* mask;
@@ -378,8 +383,10 @@ __global__ void __launch_bounds__(kProducerThreads) pack_b_kernel(const float* _
 
 // ------------------------------------------------------------------------------------------ kernel
 // BN: accumulator width (columns of the output tile), multiple of 32, <= 256.  NPASS: 1 or 3.
-template <int BN, int NPASS>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
+// EPI: the fused bias / ReLU / mask epilogue is compiled in (a separate instantiation: the plain kernel keeps the
+// leaner epilogue and register allocation the streaming PGE products were tuned with).
+template <int BN, int NPASS, bool EPI>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p, Epi ep) {
   constexpr bool kWithLo = NPASS == 3;
   constexpr int kPlanes = kWithLo ? 2 : 1;
   constexpr uint32_t kABytes = BM * BK * 2;      // one bf16 plane of the A tile
@@ -548,62 +555,105 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p) {
                           __uint_as_float(r[j + 3]));
         __syncwarp();
         const int c4 = (lane & 7) * 4, rsub = lane >> 3;
-        if (vec_c) {
-          const int gcol = nb * BN + c0 + c4;
-          float* cbase = p.C + (int64_t)(row_base + rsub) * p.ldc + tl.c_col + gcol;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) {
-            const float* bp = p.bias + gcol;
-            if ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) bv = __ldg(reinterpret_cast<const float4*>(bp));
-            else bv = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
-          }
-          const bool vec_m = p.mask && ((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
+        if constexpr (!EPI) {
+          if (vec_c) {
+            float* cbase = p.C + (int64_t)(row_base + rsub) * p.ldc + tl.c_col + nb * BN + c0 + c4;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 v = *reinterpret_cast<const float4*>(st + (rsub + 4 * i) * 36 + c4);
-            float* c = cbase + (int64_t)(4 * i) * p.ldc;
-            v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
-            if (use_atomics) {
-              atomicAdd(reinterpret_cast<float4*>(c), v);
-            } else {
-              if (p.beta != 0.f) {
-                const float4 o = *reinterpret_cast<const float4*>(c);
-                v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y);
-                v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
+            for (int i = 0; i < 8; ++i) {
+              float4 v = *reinterpret_cast<const float4*>(st + (rsub + 4 * i) * 36 + c4);
+              float* c = cbase + (int64_t)(4 * i) * p.ldc;
+              v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+              if (use_atomics) {
+                atomicAdd(reinterpret_cast<float4*>(c), v);
+              } else {
+                if (p.beta != 0.f) {
+                  const float4 o = *reinterpret_cast<const float4*>(c);
+                  v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y);
+                  v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
+                }
+                *reinterpret_cast<float4*>(c) = v;
               }
-              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-              if (p.relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+          } else {
+            for (int i = 0; i < 8; ++i) {
+              const int row = row_base + rsub + 4 * i;
+              if (row >= p.M) break;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int gc = nb * BN + c0 + c4 + e;
+                if (gc >= p.N) break;
+                float* c = p.C + (int64_t)row * p.ldc + tl.c_col + gc;
+                const float v = p.alpha * st[(rsub + 4 * i) * 36 + c4 + e];
+                if (use_atomics) {
+                  atomicAdd(c, v);
+                } else if (p.beta == 0.f) {
+                  *c = v;
+                } else {
+                  *c = fmaf(p.beta, *c, v);
+                }
               }
-              if (p.mask) {
-                const float* mp = p.mask + (int64_t)(row_base + rsub + 4 * i) * p.ldmask + gcol;
-                float4 m;
-                if (vec_m) m = __ldg(reinterpret_cast<const float4*>(mp));
-                else m = make_float4(__ldg(mp), __ldg(mp + 1), __ldg(mp + 2), __ldg(mp + 3));
-                v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
-                v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
-              }
-              *reinterpret_cast<float4*>(c) = v;
             }
           }
         } else {
-          for (int i = 0; i < 8; ++i) {
-            const int row = row_base + rsub + 4 * i;
-            if (row >= p.M) break;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int gc = nb * BN + c0 + c4 + e;
-              if (gc >= p.N) break;
-              float* c = p.C + (int64_t)row * p.ldc + tl.c_col + gc;
-              float v = p.alpha * st[(rsub + 4 * i) * 36 + c4 + e];
+          if (vec_c) {
+            const int gcol = nb * BN + c0 + c4;
+            float* cbase = p.C + (int64_t)(row_base + rsub) * p.ldc + tl.c_col + gcol;
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI && ep.bias) {
+              const float* bp = ep.bias + gcol;
+              if ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) bv = __ldg(reinterpret_cast<const float4*>(bp));
+              else bv = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+            }
+            const bool vec_m = EPI && ep.mask && ((ep.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0);
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 v = *reinterpret_cast<const float4*>(st + (rsub + 4 * i) * 36 + c4);
+              float* c = cbase + (int64_t)(4 * i) * p.ldc;
+              v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
               if (use_atomics) {
-                atomicAdd(c, v);
+                atomicAdd(reinterpret_cast<float4*>(c), v);
               } else {
-                if (p.beta != 0.f) v = fmaf(p.beta, *c, v);
-                if (p.bias) v += __ldg(p.bias + gc);
-                if (p.relu) v = fmaxf(v, 0.f);
-                if (p.mask) v = __ldg(p.mask + (int64_t)row * p.ldmask + gc) > 0.f ? v : 0.f;
-                *c = v;
+                if (p.beta != 0.f) {
+                  const float4 o = *reinterpret_cast<const float4*>(c);
+                  v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y);
+                  v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
+                }
+                if (EPI) {
+                  v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                }
+                if (EPI && ep.relu) {
+                  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                }
+                if (EPI && ep.mask) {
+                  const float* mp = ep.mask + (int64_t)(row_base + rsub + 4 * i) * ep.ldmask + gcol;
+                  float4 m;
+                  if (vec_m) m = __ldg(reinterpret_cast<const float4*>(mp));
+                  else m = make_float4(__ldg(mp), __ldg(mp + 1), __ldg(mp + 2), __ldg(mp + 3));
+                  v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+                  v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                }
+                *reinterpret_cast<float4*>(c) = v;
+              }
+            }
+          } else {
+            for (int i = 0; i < 8; ++i) {
+              const int row = row_base + rsub + 4 * i;
+              if (row >= p.M) break;
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int gc = nb * BN + c0 + c4 + e;
+                if (gc >= p.N) break;
+                float* c = p.C + (int64_t)row * p.ldc + tl.c_col + gc;
+                float v = p.alpha * st[(rsub + 4 * i) * 36 + c4 + e];
+                if (use_atomics) {
+                  atomicAdd(c, v);
+                } else {
+                  if (p.beta != 0.f) v = fmaf(p.beta, *c, v);
+                  if (EPI && ep.bias) v += __ldg(ep.bias + gc);
+                  if (EPI && ep.relu) v = fmaxf(v, 0.f);
+                  if (EPI && ep.mask) v = __ldg(ep.mask + (int64_t)row * ep.ldmask + gc) > 0.f ? v : 0.f;
+                  *c = v;
+                }
               }
             }
           }
@@ -631,14 +681,15 @@ __global__ void scale_matrix_tc_kernel(int M, int N, float* C, int64_t ldc, floa
 }
 
 // Tuning knobs for small products (read once): GS_TC_MIN_KB = fewest 64-wide k-blocks a K split may be left with
-// (default 2), GS_TC_SHRINK_BN = 1 lets small problems use narrower accumulator tiles so that more CTAs share them.
+// (default 4), GS_TC_SHRINK_BN = 1 lets small problems (K <= 2048) use narrower accumulator tiles so that more CTAs
+// share them.
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
 static int tune_min_kb() {
   static int v = -1;
-  if (v < 0) v = std::max(1, env_int("GS_TC_MIN_KB", 2));
+  if (v < 0) v = std::max(1, env_int("GS_TC_MIN_KB", 4));
   return v;
 }
 static int tune_shrink_bn() {
@@ -648,7 +699,7 @@ static int tune_shrink_bn() {
 }
 
 template <int BN, int NPASS>
-static int launch(Params& p, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+static int launch(Params& p, const Epi& ep, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
   constexpr int kPlanes = NPASS == 3 ? 2 : 1;
   constexpr bool kWithLo = NPASS == 3;
   constexpr size_t smem = (size_t)kStages * kPlanes * (BM * BK * 2 + BN * BK * 2) + 4 * 32 * 36 * 4 + 1024;
@@ -680,7 +731,9 @@ static int launch(Params& p, void* workspace, int64_t workspace_bytes, cudaStrea
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tc)", e);
       return (int)e;
@@ -707,7 +760,7 @@ static int launch(Params& p, void* workspace, int64_t workspace_bytes, cudaStrea
     // split K when the output tiles alone cannot occupy the SMs
     int splits = 1;
     const int min_kb = tune_min_kb();
-    if (mn_tiles < kNumSMs && kblocks >= 2 * min_kb && !p.bias && !p.relu && !p.mask) {
+    if (mn_tiles < kNumSMs && kblocks >= 2 * min_kb && !ep.bias && !ep.relu && !ep.mask) {
       splits = (int)((kNumSMs + mn_tiles - 1) / mn_tiles);
       if (splits > kblocks / min_kb) splits = kblocks / min_kb;
       if (splits < 1) splits = 1;
@@ -725,7 +778,8 @@ static int launch(Params& p, void* workspace, int64_t workspace_bytes, cudaStrea
     total = mn_tiles * splits;
   }
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  gemm_tc_kernel<BN, NPASS><<<grid, kThreads, smem, st>>>(p);
+  if (ep.bias || ep.relu || ep.mask) gemm_tc_kernel<BN, NPASS, true><<<grid, kThreads, smem, st>>>(p, ep);
+  else gemm_tc_kernel<BN, NPASS, false><<<grid, kThreads, smem, st>>>(p, ep);
   return finish_launch("gemm_tc");
 }
 
@@ -737,9 +791,11 @@ static inline int tc_bn_wide(int N) { return N > 128 ? 256 : (N > 64 ? 128 : (N 
 // accumulator width: the widest tile that does not waste more than half of its columns -- narrowed for small problems
 // until the output tiles cover about half of the SMs (a 909 x 256 product is 8 tiles at BN = 256 but 64 at BN = 32;
 // the A conversion repeated per column tile is negligible at that size, the serial epilogue per CTA is not)
-static inline int tc_bn(int M, int N) {
+static inline int tc_bn(int M, int N, int K) {
   int bn = tc_bn_wide(N);
-  if (!tc::tune_shrink_bn()) return bn;
+  // only for products whose A operand is small: every extra column tile converts A again, and a long K is better
+  // covered by the K split (the N'^2-deep dW product of PGE must stay at one column tile)
+  if (!tc::tune_shrink_bn() || K > 2048) return bn;
   const int64_t tm = (M + tc::BM - 1) / tc::BM;
   while (bn > 32 && tm * ((N + bn - 1) / bn) < kNumSMs / 2 && (N + bn / 2 - 1) / (bn / 2) > (N + bn - 1) / bn) bn >>= 1;
   return bn;
@@ -761,18 +817,18 @@ int gemm_tc_dispatch(int ta, int tb, int M, int N, int K, float alpha, const flo
                      int64_t workspace_bytes, const float* bias, int relu, const float* mask, int64_t ldmask,
                      cudaStream_t st) {
   if (!gemm_tc_covers(M, N, K)) return GS_ENOSYS;
-  tc::Params p{ta, tb, M, N, K, alpha, beta, A, lda, B, ldb, nullptr, C, ldc, 1, K, 0, 0, nullptr, nullptr, 0,
-               bias, relu, mask, ldmask};
+  tc::Params p{ta, tb, M, N, K, alpha, beta, A, lda, B, ldb, nullptr, C, ldc, 1, K, 0, 0, nullptr, nullptr, 0};
+  const tc::Epi ep{bias, relu, mask, ldmask};
   const bool three = precision == 1;
-  switch (tc_bn(M, N)) {
+  switch (tc_bn(M, N, K)) {
     case 256:
-      return three ? tc::launch<256, 3>(p, workspace, workspace_bytes, st) : tc::launch<256, 1>(p, workspace, workspace_bytes, st);
+      return three ? tc::launch<256, 3>(p, ep, workspace, workspace_bytes, st) : tc::launch<256, 1>(p, ep, workspace, workspace_bytes, st);
     case 128:
-      return three ? tc::launch<128, 3>(p, workspace, workspace_bytes, st) : tc::launch<128, 1>(p, workspace, workspace_bytes, st);
+      return three ? tc::launch<128, 3>(p, ep, workspace, workspace_bytes, st) : tc::launch<128, 1>(p, ep, workspace, workspace_bytes, st);
     case 64:
-      return three ? tc::launch<64, 3>(p, workspace, workspace_bytes, st) : tc::launch<64, 1>(p, workspace, workspace_bytes, st);
+      return three ? tc::launch<64, 3>(p, ep, workspace, workspace_bytes, st) : tc::launch<64, 1>(p, ep, workspace, workspace_bytes, st);
     default:
-      return three ? tc::launch<32, 3>(p, workspace, workspace_bytes, st) : tc::launch<32, 1>(p, workspace, workspace_bytes, st);
+      return three ? tc::launch<32, 3>(p, ep, workspace, workspace_bytes, st) : tc::launch<32, 1>(p, ep, workspace, workspace_bytes, st);
   }
 }
 
@@ -783,18 +839,18 @@ int gemm_tc_grouped_dispatch(int G, const int32_t* seg, const int32_t* out_block
                              const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                              int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
   if (!gemm_tc_covers(M, N, K_total) || M < 8) return GS_ENOSYS;
-  tc::Params p{1, 0, M, N, K_total, 1.f, 0.f, A, lda, B, ldb, nullptr, C, ldc, 1, K_total, 0, 0, seg, out_block, G,
-               nullptr, 0, nullptr, 0};
+  tc::Params p{1, 0, M, N, K_total, 1.f, 0.f, A, lda, B, ldb, nullptr, C, ldc, 1, K_total, 0, 0, seg, out_block, G};
+  const tc::Epi ep{nullptr, 0, nullptr, 0};
   const bool three = precision == 1;
   switch (tc_bn_wide(N)) {
     case 256:
-      return three ? tc::launch<256, 3>(p, workspace, workspace_bytes, st) : tc::launch<256, 1>(p, workspace, workspace_bytes, st);
+      return three ? tc::launch<256, 3>(p, ep, workspace, workspace_bytes, st) : tc::launch<256, 1>(p, ep, workspace, workspace_bytes, st);
     case 128:
-      return three ? tc::launch<128, 3>(p, workspace, workspace_bytes, st) : tc::launch<128, 1>(p, workspace, workspace_bytes, st);
+      return three ? tc::launch<128, 3>(p, ep, workspace, workspace_bytes, st) : tc::launch<128, 1>(p, ep, workspace, workspace_bytes, st);
     case 64:
-      return three ? tc::launch<64, 3>(p, workspace, workspace_bytes, st) : tc::launch<64, 1>(p, workspace, workspace_bytes, st);
+      return three ? tc::launch<64, 3>(p, ep, workspace, workspace_bytes, st) : tc::launch<64, 1>(p, ep, workspace, workspace_bytes, st);
     default:
-      return three ? tc::launch<32, 3>(p, workspace, workspace_bytes, st) : tc::launch<32, 1>(p, workspace, workspace_bytes, st);
+      return three ? tc::launch<32, 3>(p, ep, workspace, workspace_bytes, st) : tc::launch<32, 1>(p, ep, workspace, workspace_bytes, st);
   }
 }
 

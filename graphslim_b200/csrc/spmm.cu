@@ -29,7 +29,7 @@
 namespace gs {
 
 constexpr int kWarpsPerBlock = 8;
-constexpr int kWideWarpsPerBlock = 8;   // default of the wide kernel (see GS_SPMM_WPB)
+constexpr int kWideWarpsPerBlock = 8;   // default of the wide kernel (gs_spmm_set_tuning: wpb)
 
 template <int VEC>
 struct V;
@@ -70,6 +70,19 @@ struct V<1> {
   static __device__ __forceinline__ void atomic_add(float* p, T v) { atomicAdd(p, v); }
 };
 
+// sequential streams (rowptr, col, val): pull 256 B into the L2 per miss so that the neighbouring warps' reads of the
+// same stream are L2 hits instead of another DRAM round trip in front of their gathers
+__device__ __forceinline__ int32_t ld_seq(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.global.nc.L2::256B.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_seq(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 // Work items: [0, n_rows) = one row each (direct store); [n_rows, n_rows + n_chunks) = slices of the long rows
 // (degree > long_thr), accumulated with atomics into rows the caller has zeroed.  Row items skip long rows.
 struct Items {
@@ -103,7 +116,8 @@ __device__ __forceinline__ bool item_range(const Items& it, int i, int& row, int
 template <int VEC, int NV, int WPB, int UNR>
 __global__ void __launch_bounds__(WPB * 32)
 spmm_wide_kernel(Items it, const int32_t* __restrict__ col, const float* __restrict__ val,
-                 const float* __restrict__ X, int64_t ldx, int L, float* __restrict__ Y, int64_t ldy, int mode) {
+                 const float* __restrict__ X, int64_t ldx, int L, float* __restrict__ Y, int64_t ldy, int mode,
+                 int flags) {
   using VT = typename V<VEC>::T;
   __shared__ int32_t s_col[WPB][32];
   __shared__ float s_val[WPB][32];
@@ -112,7 +126,15 @@ spmm_wide_kernel(Items it, const int32_t* __restrict__ col, const float* __restr
   if (item >= it.n_items) return;
   int row, beg, end;
   bool atomic;
-  if (!item_range(it, item, row, beg, end, atomic)) return;
+  if ((flags & 4) && item < it.n_rows) {
+    row = item;
+    beg = ld_seq(it.rowptr + item);
+    end = ld_seq(it.rowptr + item + 1);
+    atomic = false;
+    if (it.chunk_row && end - beg > it.long_thr) return;
+  } else if (!item_range(it, item, row, beg, end, atomic)) {
+    return;
+  }
   if (atomic) mode = 2;
   const int tile0 = blockIdx.y * (32 * NV);  // first vector column of this tile
   VT acc[NV];
@@ -126,8 +148,16 @@ spmm_wide_kernel(Items it, const int32_t* __restrict__ col, const float* __restr
     const int cnt = min(32, end - base);
     __syncwarp();
     if (lane < cnt) {
-      s_col[warp][lane] = __ldg(col + base + lane);
-      s_val[warp][lane] = __ldg(val + base + lane);
+      if (flags & 4) {
+        s_col[warp][lane] = ld_seq(col + base + lane);
+        s_val[warp][lane] = ld_seq(val + base + lane);
+      } else if (flags & 2) {
+        s_col[warp][lane] = __ldcs(col + base + lane);
+        s_val[warp][lane] = __ldcs(val + base + lane);
+      } else {
+        s_col[warp][lane] = __ldg(col + base + lane);
+        s_val[warp][lane] = __ldg(val + base + lane);
+      }
     }
     __syncwarp();
 #pragma unroll UNR
@@ -149,6 +179,8 @@ spmm_wide_kernel(Items it, const int32_t* __restrict__ col, const float* __restr
       V<VEC>::atomic_add(p, acc[v]);
     } else if (mode == 1) {
       V<VEC>::st(p, V<VEC>::add(V<VEC>::ldrw(p), acc[v]));
+    } else if (flags & 1) {
+      V<VEC>::stcs(p, acc[v]);
     } else {
       V<VEC>::st(p, acc[v]);
     }
@@ -195,14 +227,20 @@ spmm_narrow_kernel(Items it, const int32_t* __restrict__ col, const float* __res
 // v2: pipelined multi-item warps (see the header comment).
 struct Tuning {
   int impl;    // 1 | 2
-  int unr;     // 0 = by width, else 2 | 4 | 8
-  int group;   // 0 = by problem size, else items per warp (1..32)
-  int flags;   // bit0: streaming stores of Y, bit1: evict-first loads of (col,val)
+  int unr;     // 0 = by kernel generation / width, else 2 | 4 | 8
+  int group;   // v2: 0 = by problem size, else items per warp (1..32)
+  int flags;   // bit0: streaming stores of Y, bit1: evict-first loads of (col,val), bit2 (v1): 256 B L2 prefetch on
+               // the sequential streams (rowptr, col, val)
+  int wpb;     // v1: warps per CTA (8 | 4 | 2)
+  int max_nv;  // v1: widest column tile in units of 32 float4 (8 | 4 | 2 | 1); narrower tiles = fewer registers, more warps
 };
+// Measured on B200 (profiles/r1_spmm_sweep_v3.json): occupancy beats per-warp pipelining for this gather -- the
+// 32-register v1 kernel with 64 resident warps per SM is 1.4-3.7x faster than v2 at every sweep point, so v1 is the
+// default and v2 stays as the documented negative result behind the knob.
 static Tuning env_tuning() {
-  Tuning t{2, 0, 0, 3};
-  const char* e = getenv("GS_SPMM_IMPL");     // escape hatch for A/B runs: 1 selects the v1 kernel process-wide
-  if (e && atoi(e) == 1) t = Tuning{1, 4, 0, 0};
+  Tuning t{1, 4, 0, 0, 8, 8};
+  const char* e = getenv("GS_SPMM_IMPL");     // escape hatch for A/B runs
+  if (e && atoi(e) == 2) t = Tuning{2, 0, 0, 3, 8, 8};
   return t;
 }
 static Tuning g_tune = env_tuning();
@@ -376,7 +414,8 @@ static int launch_spmm(const Items& it, const int32_t* col, const float* val, co
     spmm_narrow_kernel<VEC><<<gx, kWarpsPerBlock * 32, 0, st>>>(it, col, val, X, ldx, L, LPG, Y, ldy, mode);
     return finish_launch("spmm_narrow");
   }
-  const int ntiles = (L + 255) / 256;
+  const int tile_w = 32 * (g_tune.impl == 1 ? max(1, min(g_tune.max_nv, 8)) : 8);   // float4 columns per tile
+  const int ntiles = (L + tile_w - 1) / tile_w;
   const int per_tile = (L + ntiles - 1) / ntiles;
   const int nv = (per_tile + 31) / 32;
   if (g_tune.impl == 2) {
@@ -390,19 +429,12 @@ static int launch_spmm(const Items& it, const int32_t* col, const float* val, co
     }
     return finish_launch("spmm_wide_v2");
   }
-  // GS_SPMM_WPB (8|4|2) and GS_SPMM_UNR (4|8): tuning knobs of the wide kernel, read once
-  static int wpb = 0, unr = 0;
-  if (wpb == 0) {
-    const char* e = getenv("GS_SPMM_WPB");
-    wpb = e ? atoi(e) : kWideWarpsPerBlock;
-    if (wpb != 8 && wpb != 4 && wpb != 2) wpb = kWideWarpsPerBlock;
-    const char* u = getenv("GS_SPMM_UNR");
-    unr = (u && atoi(u) == 8) ? 8 : 4;
-  }
+  const int wpb = (g_tune.wpb == 4 || g_tune.wpb == 2) ? g_tune.wpb : kWideWarpsPerBlock;
+  const int unr = g_tune.unr == 8 ? 8 : 4;
   const int gxw = (it.n_items + wpb - 1) / wpb;
   dim3 grid(gxw, (L + 32 * nv - 1) / (32 * nv));
 #define GS_SPMM_LAUNCH(NVV, W, U) \
-  spmm_wide_kernel<VEC, NVV, W, U><<<grid, W * 32, 0, st>>>(it, col, val, X, ldx, L, Y, ldy, mode)
+  spmm_wide_kernel<VEC, NVV, W, U><<<grid, W * 32, 0, st>>>(it, col, val, X, ldx, L, Y, ldy, mode, g_tune.flags)
 #define GS_SPMM_CASE(NVV)                                              \
   case NVV:                                                            \
     if (unr == 8) {                                                    \
@@ -523,10 +555,11 @@ int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, c
   return gs::launch_spmm<1>(it, col, val, X, ldx, F, Y, ldy, mode, st);
 }
 
-int gs_spmm_set_tuning(int impl, int unr, int group, int flags) {
+int gs_spmm_set_tuning(int impl, int unr, int group, int flags, int wpb, int max_nv) {
   GS_REQUIRE((impl == 1 || impl == 2) && (unr == 0 || unr == 2 || unr == 4 || unr == 8) && group >= 0 && group <= 32 &&
-             flags >= 0 && flags <= 3);
-  gs::g_tune = gs::Tuning{impl, unr, group, flags};
+             flags >= 0 && flags <= 7 && (wpb == 8 || wpb == 4 || wpb == 2) &&
+             (max_nv == 8 || max_nv == 4 || max_nv == 2 || max_nv == 1));
+  gs::g_tune = gs::Tuning{impl, unr, group, flags, wpb, max_nv};
   return GS_OK;
 }
 

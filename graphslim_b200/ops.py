@@ -209,9 +209,11 @@ class CudaOps:
                                             _ptr(cb), _ptr(ce), self.stream), "gs_spmm_csr_f32")
         return out
 
-    def spmm_set_tuning(self, impl=2, unr=0, group=0, flags=3):
-        """Kernel generation / in-flight gathers / rows per warp / cache hints of the wide SpMM (include/graphslim_b200.h)."""
-        _lib.check(self.lib.gs_spmm_set_tuning(int(impl), int(unr), int(group), int(flags)), "gs_spmm_set_tuning")
+    def spmm_set_tuning(self, impl=1, unr=4, group=0, flags=0, wpb=8, max_nv=8):
+        """Kernel generation / gathers in flight / rows per warp (v2) / cache hints / warps per CTA and widest column
+        tile (v1) of the wide SpMM (include/graphslim_b200.h).  The defaults are the library's."""
+        _lib.check(self.lib.gs_spmm_set_tuning(int(impl), int(unr), int(group), int(flags), int(wpb), int(max_nv)),
+                   "gs_spmm_set_tuning")
 
     def spmm_scatter(self, csr, dY, out):
         """out[col[e],:] += val[e]*dY[row(e),:] (atomics); `out` must be pre-initialised."""

@@ -56,23 +56,17 @@ def powerlaw_csr(n, nnz_target, seed, dev):
     return rowptr.to(torch.int32), col.to(torch.int32), val
 
 
-VARIANTS = {   # gs_spmm_set_tuning(impl, unr, group, flags, wpb, max_nv)
-    "v1": (1, 4, 0, 0, 8, 8),
-    "v1_unr8": (1, 8, 0, 0, 8, 8),
-    "v1_wpb4": (1, 4, 0, 0, 4, 8),
-    "v1_wpb2": (1, 4, 0, 0, 2, 8),
-    "v1_wpb4_unr8": (1, 8, 0, 0, 4, 8),
-    "v1_cs": (1, 4, 0, 3, 8, 8),
-    "v1_l2pf": (1, 4, 0, 4, 8, 8),
-    "v1_l2pf_unr8": (1, 8, 0, 4, 8, 8),
-    "v1_l2pf_cs_store": (1, 4, 0, 5, 8, 8),
-    "v1_nv4": (1, 4, 0, 0, 8, 4),
-    "v1_nv2": (1, 4, 0, 0, 8, 2),
-    "v1_nv1": (1, 4, 0, 0, 8, 1),
-    "v1_nv1_l2pf": (1, 4, 0, 4, 8, 1),
-    "v1_nv2_l2pf_unr8": (1, 8, 0, 4, 8, 2),
-    "v2": (2, 0, 0, 3, 8, 8),
-    "v2_group1": (2, 0, 1, 3, 8, 8),
+VARIANTS = {   # gs_spmm_set_tuning(impl, unr, group, flags, wpb, max_nv); 0 = auto
+    "v1_w8_u4": (1, 4, 0, 0, 8, 8),
+    "v1_w4_u8": (1, 8, 0, 0, 4, 8),
+    "v1_w2_u4": (1, 4, 0, 0, 2, 8),
+    "v1_w2_u8": (1, 8, 0, 0, 2, 8),
+    "v1_auto": (1, 0, 0, 0, 0, 0),
+    "v1_nv2_u8": (1, 8, 0, 0, 0, 2),
+    "v1_nv2_u8_w4": (1, 8, 0, 0, 4, 2),
+    "v1_nv2_u8_w2": (1, 8, 0, 0, 2, 2),
+    "v1_nv3_u8": (1, 8, 0, 0, 0, 4),
+    "v2": (2, 0, 0, 3, 0, 0),
 }
 
 
@@ -94,7 +88,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--variants", action="store_true", help="also time every tuning of the wide kernel (VARIANTS)")
-    ap.add_argument("--long-row", type=int, default=512, help="rows with more non-zeros are sliced (atomics)")
+    ap.add_argument("--long-row", type=int, default=128, help="rows with more non-zeros are sliced (atomics)")
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_spmm_sweep.json"))
     ns = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -136,7 +130,7 @@ def main():
                     elif not torch.equal(base, outp):
                         variants[name + "_MISMATCH"] = float((base - outp).abs().max())
                 del base
-                K.spmm_set_tuning()
+                K.spmm_auto_tuning()
             ms = time_it(lambda: K.spmm(csr, Xp, out=outp), flush)
             ref = torch.sparse.mm(tcsr, X.contiguous())
             err = float((out - ref).abs().max() / ref.abs().max())

@@ -543,6 +543,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p, Epi ep) 
                          (nb * BN + BN <= p.N) && (row_base + 32 <= p.M);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        // EPI: the mask rows (or, without a mask, the old C values of a beta != 0 product) of this 32 x 32 block are
+        // requested before the TMEM read and the staging pass, so their global-memory latency is paid once per block
+        // instead of once per row; one register array serves both uses
+        float4 pre[EPI ? 8 : 1];
+        bool pre_old = false, pre_mask = false;
+        if constexpr (EPI) {
+          if (vec_c && !use_atomics) {
+            const int c4p = (lane & 7) * 4, rsubp = lane >> 3;
+            const int gcolp = nb * BN + c0 + c4p;
+            pre_mask = ep.mask && ((ep.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0);
+            pre_old = !pre_mask && p.beta != 0.f;
+            const float* src = pre_mask ? ep.mask + (int64_t)(row_base + rsubp) * ep.ldmask + gcolp
+                                        : p.C + (int64_t)(row_base + rsubp) * p.ldc + tl.c_col + gcolp;
+            const int64_t ld = pre_mask ? ep.ldmask : p.ldc;
+            if (pre_mask || pre_old) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pre[i] = *reinterpret_cast<const float4*>(src + (int64_t)(4 * i) * ld);
+            }
+          }
+        }
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
         tmem_ld32(taddr, r);
@@ -614,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p, Epi ep) 
                 atomicAdd(reinterpret_cast<float4*>(c), v);
               } else {
                 if (p.beta != 0.f) {
-                  const float4 o = *reinterpret_cast<const float4*>(c);
+                  const float4 o = pre_old ? pre[i] : *reinterpret_cast<const float4*>(c);
                   v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y);
                   v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
                 }
@@ -627,7 +647,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p, Epi ep) 
                 if (EPI && ep.mask) {
                   const float* mp = ep.mask + (int64_t)(row_base + rsub + 4 * i) * ep.ldmask + gcol;
                   float4 m;
-                  if (vec_m) m = __ldg(reinterpret_cast<const float4*>(mp));
+                  if (pre_mask) m = pre[i];
+                  else if (vec_m) m = __ldg(reinterpret_cast<const float4*>(mp));
                   else m = make_float4(__ldg(mp), __ldg(mp + 1), __ldg(mp + 2), __ldg(mp + 3));
                   v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
                   v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
@@ -778,7 +799,9 @@ static int launch(Params& p, const Epi& ep, void* workspace, int64_t workspace_b
     total = mn_tiles * splits;
   }
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  if (ep.bias || ep.relu || ep.mask) gemm_tc_kernel<BN, NPASS, true><<<grid, kThreads, smem, st>>>(p, ep);
+  const bool plain_store = p.splits == 1 && !p.seg;
+  if (ep.bias || ep.relu || ep.mask || (plain_store && p.beta != 0.f))
+    gemm_tc_kernel<BN, NPASS, true><<<grid, kThreads, smem, st>>>(p, ep);
   else gemm_tc_kernel<BN, NPASS, false><<<grid, kThreads, smem, st>>>(p, ep);
   return finish_launch("gemm_tc");
 }

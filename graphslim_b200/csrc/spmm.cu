@@ -29,7 +29,6 @@
 namespace gs {
 
 constexpr int kWarpsPerBlock = 8;
-constexpr int kWideWarpsPerBlock = 8;   // default of the wide kernel (gs_spmm_set_tuning: wpb)
 
 template <int VEC>
 struct V;
@@ -237,10 +236,14 @@ struct Tuning {
 // Measured on B200 (profiles/r1_spmm_sweep_v3.json): occupancy beats per-warp pipelining for this gather -- the
 // 32-register v1 kernel with 64 resident warps per SM is 1.4-3.7x faster than v2 at every sweep point, so v1 is the
 // default and v2 stays as the documented negative result behind the knob.
+// Auto settings (0) of v1, from profiles/r1_spmm_sweep_v3.json: one column tile (F <= 128 floats) -> 4-warp CTAs with
+// 8 gathers in flight (1.15-1.28x over 8 warps / 4 gathers); wider rows -> 2-warp CTAs, 4 gathers (1.05-1.12x).  Dense
+// graphs with wide rows additionally gain 1.2x from 64-float4 column tiles (max_nv = 2, unr = 8), which the host
+// wrapper selects from nnz / n_rows -- the C entry point does not know nnz without a device read.
 static Tuning env_tuning() {
-  Tuning t{1, 4, 0, 0, 8, 8};
+  Tuning t{1, 0, 0, 0, 0, 0};
   const char* e = getenv("GS_SPMM_IMPL");     // escape hatch for A/B runs
-  if (e && atoi(e) == 2) t = Tuning{2, 0, 0, 3, 8, 8};
+  if (e && atoi(e) == 2) t = Tuning{2, 0, 0, 3, 0, 0};
   return t;
 }
 static Tuning g_tune = env_tuning();
@@ -414,7 +417,8 @@ static int launch_spmm(const Items& it, const int32_t* col, const float* val, co
     spmm_narrow_kernel<VEC><<<gx, kWarpsPerBlock * 32, 0, st>>>(it, col, val, X, ldx, L, LPG, Y, ldy, mode);
     return finish_launch("spmm_narrow");
   }
-  const int tile_w = 32 * (g_tune.impl == 1 ? max(1, min(g_tune.max_nv, 8)) : 8);   // float4 columns per tile
+  const int max_nv = (g_tune.impl == 1 && g_tune.max_nv > 0) ? min(g_tune.max_nv, 8) : 8;
+  const int tile_w = 32 * max_nv;                                                     // float4 columns per tile
   const int ntiles = (L + tile_w - 1) / tile_w;
   const int per_tile = (L + ntiles - 1) / ntiles;
   const int nv = (per_tile + 31) / 32;
@@ -429,8 +433,8 @@ static int launch_spmm(const Items& it, const int32_t* col, const float* val, co
     }
     return finish_launch("spmm_wide_v2");
   }
-  const int wpb = (g_tune.wpb == 4 || g_tune.wpb == 2) ? g_tune.wpb : kWideWarpsPerBlock;
-  const int unr = g_tune.unr == 8 ? 8 : 4;
+  const int wpb = g_tune.wpb > 0 ? g_tune.wpb : (nv == 1 ? 4 : 2);
+  const int unr = g_tune.unr > 0 ? (g_tune.unr == 8 ? 8 : 4) : (nv == 1 ? 8 : 4);
   const int gxw = (it.n_items + wpb - 1) / wpb;
   dim3 grid(gxw, (L + 32 * nv - 1) / (32 * nv));
 #define GS_SPMM_LAUNCH(NVV, W, U) \
@@ -557,8 +561,8 @@ int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, c
 
 int gs_spmm_set_tuning(int impl, int unr, int group, int flags, int wpb, int max_nv) {
   GS_REQUIRE((impl == 1 || impl == 2) && (unr == 0 || unr == 2 || unr == 4 || unr == 8) && group >= 0 && group <= 32 &&
-             flags >= 0 && flags <= 7 && (wpb == 8 || wpb == 4 || wpb == 2) &&
-             (max_nv == 8 || max_nv == 4 || max_nv == 2 || max_nv == 1));
+             flags >= 0 && flags <= 7 && (wpb == 0 || wpb == 8 || wpb == 4 || wpb == 2) &&
+             (max_nv == 0 || max_nv == 8 || max_nv == 4 || max_nv == 2 || max_nv == 1));
   gs::g_tune = gs::Tuning{impl, unr, group, flags, wpb, max_nv};
   return GS_OK;
 }

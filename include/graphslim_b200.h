@@ -55,12 +55,14 @@ int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, c
 /* Tuning of the wide (F >= 128) SpMM kernel; process-wide, not thread-safe against concurrent launches.
  *   impl   1 = one row per warp, (col,val) staged in shared memory (default: fastest at every measured point);
  *          2 = pipelined multi-row warps (kept as a measured negative result: registers cost too much occupancy)
- *   unr    feature-row gathers in flight per warp (impl 1: 4|8, 0 = 4; impl 2: 0 = chosen from the width, else 2|4|8)
+ *   unr    feature-row gathers in flight per warp (0 = auto; impl 1: 4|8; impl 2: 2|4|8)
  *   group  work items per warp for impl 2 (0 = chosen from the problem size, else 1..32)
  *   flags  bit0 streaming stores of Y, bit1 evict-first loads of (col,val), bit2 (impl 1) 256-byte L2 prefetch on the
- *          sequential streams (rowptr, col, val)
- *   wpb    impl 1: warps per CTA (8|4|2)
- *   max_nv impl 1: widest column tile in units of 32 float4 (8|4|2|1); narrower tiles use fewer registers per warp
+ *          sequential streams (rowptr, col, val)  -- none of them moved a measured point by more than 2 %
+ *   wpb    impl 1: warps per CTA (0 = auto, 8|4|2)
+ *   max_nv impl 1: widest column tile in units of 32 float4 (0 = auto = 8, 8|4|2|1); narrower tiles use fewer
+ *          registers per warp and win on dense graphs with wide rows
+ * Defaults: impl 1, everything else auto.
  * Every setting produces the same bits (CSR-order fmaf accumulation); no reference counterpart. */
 int gs_spmm_set_tuning(int impl, int unr, int group, int flags, int wpb, int max_nv);
 

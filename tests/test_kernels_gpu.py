@@ -141,7 +141,8 @@ def test_spmm_tunings_bit_identical(K, F):
                      torch.from_numpy(val), n_rows, n_cols), "cuda")
     X = torch.from_numpy(gen.standard_normal((n_cols, F)).astype(np.float32)).cuda()
     base0 = torch.from_numpy(gen.standard_normal((n_rows, F)).astype(np.float32)).cuda()
-    tunings = [(1, 4, 0, 0, 8, 8), (1, 8, 0, 3, 4, 8), (1, 4, 0, 4, 2, 4), (1, 8, 0, 7, 8, 2), (1, 4, 0, 5, 4, 1),
+    tunings = [(1, 4, 0, 0, 8, 8), (1, 0, 0, 0, 0, 0), (1, 8, 0, 3, 4, 8), (1, 4, 0, 4, 2, 4), (1, 8, 0, 7, 8, 2),
+               (1, 4, 0, 5, 4, 1),
                (2, 0, 0, 3, 8, 8), (2, 2, 0, 3, 8, 8), (2, 4, 1, 0, 8, 8), (2, 8, 3, 1, 8, 8), (2, 0, 16, 2, 8, 8),
                (2, 4, 32, 3, 8, 8)]
     try:
@@ -163,7 +164,7 @@ def test_spmm_tunings_bit_identical(K, F):
         sub = Csr(csr.rowptr[:301].cpu(), csr.col.cpu(), csr.val.cpu(), 300, n_cols)
         assert torch.equal(outs[0][0][:300].cpu(), _spmm_seq_fp32(sub, X.cpu()))
     finally:
-        K.spmm_set_tuning()
+        K.spmm_auto_tuning()
 
 
 def test_spmm_transpose_and_scatter_agree(K, E):

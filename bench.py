@@ -166,8 +166,8 @@ def spmm_probe(agent, pk, iters=10):
     n, F = X.shape
     base = agent.adj_csr
     nnz = base.col.numel()
-    # power-law rows (max degree 1e4-1e5) are split into <=128-nnz work items
-    chunks = chunks_to_device(build_row_chunks(base.rowptr.cpu().numpy(), 128), K.device)
+    # power-law rows (max degree 1e4-1e5) are split into <=64-nnz work items
+    chunks = chunks_to_device(build_row_chunks(base.rowptr.cpu().numpy(), 64), K.device)
     csr = Csr(base.rowptr, base.col, base.val, base.n_rows, base.n_cols, chunks)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=K.device)
     out = K.empty(n, F)

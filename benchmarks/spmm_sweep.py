@@ -88,7 +88,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--variants", action="store_true", help="also time every tuning of the wide kernel (VARIANTS)")
-    ap.add_argument("--long-row", type=int, default=128, help="rows with more non-zeros are sliced (atomics)")
+    ap.add_argument("--long-row", type=int, default=64, help="rows with more non-zeros are sliced (atomics)")
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_spmm_sweep.json"))
     ns = ap.parse_args()
     dev = torch.device("cuda:0")

@@ -2,7 +2,7 @@
 import numpy as np
 
 
-def build_row_chunks(rowptr, max_nnz=128):
+def build_row_chunks(rowptr, max_nnz=64):
     """Slices of the rows with more than ``max_nnz`` non-zeros: int32 arrays (row, begin, end) and the threshold.
 
     A 1e4-1e5-degree hub of a power-law graph would otherwise serialise on one warp; the SpMM kernel clears those rows

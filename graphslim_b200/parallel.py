@@ -108,7 +108,7 @@ class RowPartitionedSpmm:
     """
 
     def __init__(self, rowptr, col, val, *, rank, world, group=None, device="cuda", make_csr=None, spmm=None,
-                 n_slabs=4, long_row_nnz=128):
+                 n_slabs=4, long_row_nnz=64):
         import scipy.sparse as sp
         rowptr = np.asarray(rowptr, dtype=np.int64)
         col = np.asarray(col, dtype=np.int64)

@@ -29,7 +29,7 @@ if len(sys.argv) > 1:
     cases = [cases[int(a)] for a in sys.argv[1:]]
 for n, nnz_t, F in cases:
     rowptr, col, val = powerlaw_csr(n, nnz_t, seed=7, dev=dev)
-    chunks = chunks_to_device(build_row_chunks(rowptr.cpu().numpy(), 128), dev)
+    chunks = chunks_to_device(build_row_chunks(rowptr.cpu().numpy(), 64), dev)
     csr = Csr(rowptr, col, val, n, n, chunks)
     ld = (F + 7) // 8 * 8
     X = torch.zeros(n, ld, device=dev)

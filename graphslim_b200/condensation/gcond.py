@@ -4,7 +4,7 @@ from tqdm import trange
 
 from .. import engine as _engine
 from ..dataset_utils import verbose_time_memory
-from .gcond_base import GCondBase, _Adam
+from .gcond_base import GCondBase, InnerLoop
 
 
 class GCond(GCondBase):
@@ -35,6 +35,10 @@ class GCond(GCondBase):
         self.draw_model_weights(self.model)                   # constructor draw (model = SGC(...), gcond.py:38)
         if self.x_variant:
             self.adj_syn = torch.eye(self.nnodes_syn, device=K.device)      # gcondx.py:32
+        outer_loop, inner_loop = self.get_loops(args)
+        # traced runs (parity tests read intermediate tensors) stay on the step-by-step path
+        self.inner = InnerLoop(K, self.model, self.feat_syn, self.nnodes_syn, args.lr, outer_loop * inner_loop,
+                               use_graph=getattr(args, "cuda_graphs", True) and self.trace is None)
         self.loss_avg, self.best_val = 0, 0
         self.adj_syn_inner = None
         self._pge_ready = None
@@ -43,17 +47,16 @@ class GCond(GCondBase):
     def run_epoch(self, it):
         args, K, pge, model = self.args, self.K, self.pge, self.model
         outer_loop, inner_loop = self.get_loops(args)
-        W = [w.to(K.device) for w in self.draw_model_weights(model)]        # model.initialize(), gcond.py:42
-        model.set_weights(W)
+        # model.initialize() (gcond.py:42) and a fresh Adam (gcond.py:44), into the inner loop's fixed buffers
+        W = self.inner.begin_epoch(self.draw_model_weights(model))
         if self.trace:
             self.trace("model_init", epoch=it, W=W)
-        optimizer_model = _Adam(K, W, args.lr)                # fresh Adam every epoch (gcond.py:44)
         self._loss_dev.zero_()
         # the epoch's class batches are sampled one outer step ahead on a worker thread (same random streams, same
         # order); nothing else draws from numpy's / torch's generators until the epoch ends
         self._prefetch = self.sampler.prefetch(outer_loop, model.lay.mask) if getattr(args, "prefetch", True) else None
         try:
-            self._run_outer_steps(it, outer_loop, inner_loop, optimizer_model)
+            self._run_outer_steps(it, outer_loop, inner_loop)
         finally:
             if self._prefetch is not None:
                 self._prefetch.join()
@@ -63,7 +66,7 @@ class GCond(GCondBase):
             # the reference's loss.item() per outer step
             self.loss_avg = (self.loss_avg + float(self._loss_dev.item())) / (self.data.nclass * outer_loop)
 
-    def _run_outer_steps(self, it, outer_loop, inner_loop, optimizer_model):
+    def _run_outer_steps(self, it, outer_loop, inner_loop):
         args, K, pge, model = self.args, self.K, self.pge, self.model
         for ol in range(outer_loop):
             if not self.x_variant:
@@ -103,8 +106,9 @@ class GCond(GCondBase):
                     adj_inner, r_inner = K.dense_gcn_norm(self.adj_syn_inner)
                     self._pge_ready = (adj_inner, r_inner)
             with K.timed("phase_inner_loop"):
+                self.inner.set_adj(adj_inner)
                 for _ in range(inner_loop):
-                    optimizer_model.step(model.train_grads(self.feat_syn, adj_inner))
+                    self.inner.step()
 
     def publish(self, data):
         n = self.nnodes_syn

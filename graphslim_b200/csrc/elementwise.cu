@@ -330,6 +330,28 @@ __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __res
   p[i] = p[i] - step_size * (mi / denom);
 }
 
+// Adam step whose two step-dependent scalars come from device memory: table[2*t] = lr / (1 - beta1^(t+1)) and
+// table[2*t+1] = sqrt(1 - beta2^(t+1)) for the zero-based step t = *step_dev.  Nothing in the launch depends on the
+// step any more, so an inner-loop iteration can be captured once in a CUDA graph and replayed.
+__global__ void adam_table_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                  float* __restrict__ v, const float* __restrict__ table,
+                                  const int32_t* __restrict__ step_dev, float om_beta1, float beta2, float om_beta2,
+                                  float eps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = *step_dev;
+  const float step_size = table[2 * t], bc2_sqrt = table[2 * t + 1];
+  const float gi = g[i];
+  const float mi = m[i] + om_beta1 * (gi - m[i]);
+  const float vi = v[i] * beta2 + (om_beta2 * gi) * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = p[i] - step_size * (mi / denom);
+}
+
+__global__ void counter_add_kernel(int32_t* c, int32_t inc) { *c += inc; }
+
 __global__ void axpby_kernel(int64_t n, float a, const float* __restrict__ x, float b, float* __restrict__ y) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -464,6 +486,32 @@ int gs_adam_step_f32(int64_t n, float* p, const float* g, float* m, float* v, in
   adam_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(n, p, g, m, v, step_size, bc2_sqrt, (float)(1.0 - beta1),
                                                             (float)beta2, (float)(1.0 - beta2), (float)eps);
   return finish_launch("adam");
+}
+
+int gs_adam_table_f32(int32_t steps, double lr, double beta1, double beta2, float* table_host) {
+  GS_REQUIRE(steps >= 0 && table_host);
+  for (int32_t t = 0; t < steps; ++t) {   // the scalar prologue of gs_adam_step_f32 for step t + 1, same roundings
+    const double bc1 = 1.0 - pow(beta1, (double)(t + 1));
+    const double bc2 = 1.0 - pow(beta2, (double)(t + 1));
+    table_host[2 * t] = (float)(lr / bc1);
+    table_host[2 * t + 1] = (float)sqrt(bc2);
+  }
+  return GS_OK;
+}
+
+int gs_adam_step_table_f32(int64_t n, float* p, const float* g, float* m, float* v, const float* table,
+                           const int32_t* step_dev, double beta1, double beta2, double eps, void* stream) {
+  GS_REQUIRE(n >= 0 && p && g && m && v && table && step_dev);
+  if (n == 0) return GS_OK;
+  adam_table_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(n, p, g, m, v, table, step_dev, (float)(1.0 - beta1),
+                                                                  (float)beta2, (float)(1.0 - beta2), (float)eps);
+  return finish_launch("adam_table");
+}
+
+int gs_counter_add_i32(int32_t* counter, int32_t inc, void* stream) {
+  GS_REQUIRE(counter);
+  counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, inc);
+  return finish_launch("counter_add");
 }
 
 int gs_axpby_f32(int64_t n, float a, const float* x, float b, float* y, void* stream) {

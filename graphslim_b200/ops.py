@@ -470,6 +470,22 @@ class CudaOps:
         _lib.check(self.lib.gs_adam_step_f32(p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), step, lr, beta1, beta2,
                                              eps, self.stream), "gs_adam_step_f32")
 
+    def adam_table(self, steps, lr, beta1=0.9, beta2=0.999):
+        """(steps x 2) device table of Adam's step-dependent scalars for steps 1..steps (see gs_adam_table_f32)."""
+        host = torch.empty(max(int(steps), 1), 2, dtype=torch.float32)
+        _lib.check(self.lib.gs_adam_table_f32(int(steps), lr, beta1, beta2, host.data_ptr()), "gs_adam_table_f32")
+        return host.to(self.device)
+
+    def adam_step_table(self, p, g, m, v, table, step_dev, beta1=0.9, beta2=0.999, eps=1e-8):
+        if not (p.is_contiguous() and g.is_contiguous()):
+            raise ValueError("adam_step_table needs contiguous tensors")
+        _lib.check(self.lib.gs_adam_step_table_f32(p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(table),
+                                                   _ptr(step_dev), beta1, beta2, eps, self.stream),
+                   "gs_adam_step_table_f32")
+
+    def counter_add(self, counter, inc=1):
+        _lib.check(self.lib.gs_counter_add_i32(_ptr(counter), int(inc), self.stream), "gs_counter_add_i32")
+
     def axpby(self, a, x, b, y):
         _lib.check(self.lib.gs_axpby_f32(y.numel(), a, _ptr(x), b, _ptr(y), self.stream), "gs_axpby_f32")
         return y

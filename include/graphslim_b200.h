@@ -220,6 +220,16 @@ int gs_pge_bn1_bwd_reduce_f32(int32_t n, int32_t h, const float* dH1, const floa
 /* ---- optimiser (torch.optim.Adam defaults; condensation/gcond_base.py:68-69, gcond.py:44) ---- */
 int gs_adam_step_f32(int64_t n, float* p, const float* g, float* m, float* v, int32_t step, double lr, double beta1,
                      double beta2, double eps, void* stream);
+/* The same step with its two step-dependent scalars read from device memory, so that a launch no longer depends on
+ * the step number and an inner-loop iteration (gcond.py:63-72) can be captured in a CUDA graph:
+ *   gs_adam_table_f32 fills table_host[2*t], table_host[2*t+1] (t = 0..steps-1) with the step_size and sqrt(bias
+ *   correction 2) that gs_adam_step_f32 computes for step t+1 (same double arithmetic, same roundings);
+ *   gs_adam_step_table_f32 applies step *step_dev (zero-based, device) from the uploaded table;
+ *   gs_counter_add_i32 advances the device step counter. */
+int gs_adam_table_f32(int32_t steps, double lr, double beta1, double beta2, float* table_host);
+int gs_adam_step_table_f32(int64_t n, float* p, const float* g, float* m, float* v, const float* table,
+                           const int32_t* step_dev, double beta1, double beta2, double eps, void* stream);
+int gs_counter_add_i32(int32_t* counter, int32_t inc, void* stream);
 /* y = a*x + b*y */
 int gs_axpby_f32(int64_t n, float a, const float* x, float b, float* y, void* stream);
 

@@ -326,6 +326,23 @@ class EmuOps:
         denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
         p.addcdiv_(m, denom, value=-(lr / bc1))
 
+    def adam_table(self, steps, lr, beta1=0.9, beta2=0.999):
+        import numpy as np
+        t = np.arange(1, max(int(steps), 1) + 1, dtype=np.float64)
+        tab = np.stack([lr / (1.0 - beta1 ** t), np.sqrt(1.0 - beta2 ** t)], 1).astype(np.float32)
+        return torch.from_numpy(tab)
+
+    def adam_step_table(self, p, g, m, v, table, step_dev, beta1=0.9, beta2=0.999, eps=1e-8):
+        t = int(step_dev.item())
+        step_size, bc2_sqrt = float(table[t, 0]), float(table[t, 1])
+        m.lerp_(g, 1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = (v.sqrt() / bc2_sqrt).add_(eps)
+        p.addcdiv_(m, denom, value=-step_size)
+
+    def counter_add(self, counter, inc=1):
+        counter.add_(int(inc))
+
     def axpby(self, a, x, b, y):
         if b == 0.0:
             y.copy_(a * x)

@@ -396,7 +396,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p, Epi ep) 
   constexpr uint32_t kIdesc = make_idesc(BM, BN);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the shared-space pointer (an integer round-trip would hand the
+  // compiler a generic pointer: LD/ST instead of LDS/STS in the producers and the epilogue, and possible aliasing
+  // between the staging tile and the global stores that serialises the epilogue's loads)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* stage_out = reinterpret_cast<float*>(smem + kStages * kStageBytes);   // 4 warps x 32 x 36 floats
   __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_holder;
@@ -578,21 +581,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p, Epi ep) 
         if constexpr (!EPI) {
           if (vec_c) {
             float* cbase = p.C + (int64_t)(row_base + rsub) * p.ldc + tl.c_col + nb * BN + c0 + c4;
+            // all eight staged rows are read back before the first global store is issued (one shared-memory
+            // round trip per block instead of eight dependent ones)
+            float4 v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float4 v = *reinterpret_cast<const float4*>(st + (rsub + 4 * i) * 36 + c4);
-              float* c = cbase + (int64_t)(4 * i) * p.ldc;
-              v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
-              if (use_atomics) {
-                atomicAdd(reinterpret_cast<float4*>(c), v);
-              } else {
-                if (p.beta != 0.f) {
-                  const float4 o = *reinterpret_cast<const float4*>(c);
-                  v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y);
-                  v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
-                }
-                *reinterpret_cast<float4*>(c) = v;
+              v[i] = *reinterpret_cast<const float4*>(st + (rsub + 4 * i) * 36 + c4);
+              v[i].x *= p.alpha; v[i].y *= p.alpha; v[i].z *= p.alpha; v[i].w *= p.alpha;
+            }
+            if (use_atomics) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<float4*>(cbase + (int64_t)(4 * i) * p.ldc), v[i]);
+            } else if (p.beta != 0.f) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float* c = cbase + (int64_t)(4 * i) * p.ldc;
+                const float4 o = *reinterpret_cast<const float4*>(c);
+                v[i].x = fmaf(p.beta, o.x, v[i].x); v[i].y = fmaf(p.beta, o.y, v[i].y);
+                v[i].z = fmaf(p.beta, o.z, v[i].z); v[i].w = fmaf(p.beta, o.w, v[i].w);
+                *reinterpret_cast<float4*>(c) = v[i];
               }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(cbase + (int64_t)(4 * i) * p.ldc) = v[i];
             }
           } else {
             for (int i = 0; i < 8; ++i) {
@@ -625,35 +636,42 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(Params p, Epi ep) 
               else bv = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
             }
             const bool vec_m = EPI && ep.mask && ((ep.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0);
-  #pragma unroll
+            float4 v[8];
+#pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float4 v = *reinterpret_cast<const float4*>(st + (rsub + 4 * i) * 36 + c4);
-              float* c = cbase + (int64_t)(4 * i) * p.ldc;
-              v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
-              if (use_atomics) {
-                atomicAdd(reinterpret_cast<float4*>(c), v);
-              } else {
+              v[i] = *reinterpret_cast<const float4*>(st + (rsub + 4 * i) * 36 + c4);
+              v[i].x *= p.alpha; v[i].y *= p.alpha; v[i].z *= p.alpha; v[i].w *= p.alpha;
+            }
+            if (use_atomics) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<float4*>(cbase + (int64_t)(4 * i) * p.ldc), v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float* c = cbase + (int64_t)(4 * i) * p.ldc;
+                float4 w = v[i];
                 if (p.beta != 0.f) {
                   const float4 o = pre_old ? pre[i] : *reinterpret_cast<const float4*>(c);
-                  v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y);
-                  v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
+                  w.x = fmaf(p.beta, o.x, w.x); w.y = fmaf(p.beta, o.y, w.y);
+                  w.z = fmaf(p.beta, o.z, w.z); w.w = fmaf(p.beta, o.w, w.w);
                 }
-                if (EPI) {
-                  v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                w.x += bv.x; w.y += bv.y; w.z += bv.z; w.w += bv.w;
+                if (ep.relu) {
+                  w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
                 }
-                if (EPI && ep.relu) {
-                  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                }
-                if (EPI && ep.mask) {
-                  const float* mp = ep.mask + (int64_t)(row_base + rsub + 4 * i) * ep.ldmask + gcol;
+                if (ep.mask) {
                   float4 m;
-                  if (pre_mask) m = pre[i];
-                  else if (vec_m) m = __ldg(reinterpret_cast<const float4*>(mp));
-                  else m = make_float4(__ldg(mp), __ldg(mp + 1), __ldg(mp + 2), __ldg(mp + 3));
-                  v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
-                  v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                  if (pre_mask) {
+                    m = pre[i];
+                  } else {
+                    const float* mp = ep.mask + (int64_t)(row_base + rsub + 4 * i) * ep.ldmask + gcol;
+                    if (vec_m) m = __ldg(reinterpret_cast<const float4*>(mp));
+                    else m = make_float4(__ldg(mp), __ldg(mp + 1), __ldg(mp + 2), __ldg(mp + 3));
+                  }
+                  w.x = m.x > 0.f ? w.x : 0.f; w.y = m.y > 0.f ? w.y : 0.f;
+                  w.z = m.z > 0.f ? w.z : 0.f; w.w = m.w > 0.f ? w.w : 0.f;
                 }
-                *reinterpret_cast<float4*>(c) = v;
+                *reinterpret_cast<float4*>(c) = w;
               }
             }
           } else {

@@ -305,11 +305,16 @@ def run_ours(ns):
     # h = 256 that is 64 flop/byte, below the bf16 ridge (sustained TF/s / HBM GB/s = ~210 flop/byte, ~70 with the
     # three MMA passes of the 3xBF16 split), so the binding roofline is HBM; the tensor-pipe figures are kept beside it.
     n_syn, h = agent.nnodes_syn, agent.pge.h
+    pge_sharded = bool(getattr(agent, "pge_sharded", False))
     roof = None
     if "pge_l2_fwd" in kernel_times and kernel_times["pge_l2_fwd"][0] > 0:
         cnt, tot = kernel_times["pge_l2_fwd"]
-        flops = 2.0 * n_syn * n_syn * h * h
-        alg_bytes = 4.0 * n_syn * n_syn * h * 2 + 4.0 * h * h
+        pair_rows = n_syn * n_syn
+        sh = getattr(agent.pge, "shard", None)
+        if sh is not None:                                   # PGE pair rows dealt to the ranks: this rank's share
+            pair_rows = sh["rows"][sh["rank"]]
+        flops = 2.0 * pair_rows * h * h
+        alg_bytes = 4.0 * pair_rows * h * 2 + 4.0 * h * h
         sec = tot / cnt / 1e3
         ach_tf = flops / sec / 1e12
         ach_gb = alg_bytes / sec / 1e9
@@ -318,7 +323,7 @@ def run_ours(ns):
         share = {k: v[1] / ms for k, v in kernel_times.items()}
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and world == 1:
             traffic = json.load(open(tpath)).get(ns.workload, {}).get("pge_l2_fwd")
         roof = {"kernel": "PGE layer-2 product (N'^2 x h x h) forward, gs_gemm_f32 precision=%d (gemm_tc_kernel)"
                           % ns.precision,
@@ -384,8 +389,9 @@ def run_ours(ns):
         "vs_baseline": None, "dtype": "f32" if ns.precision == 0 else ("bf16x3-split/f32-accum" if ns.precision == 1
                                                                          else "bf16/f32-accum"),
         "data": "synthetic",
-        "config": {"workload": WORKLOADS[ns.workload], "parallelism": f"class-sharded x{world}" if world > 1 else
-                   "single GPU", "gemm_precision": ns.precision,
+        "config": {"workload": WORKLOADS[ns.workload],
+                   "parallelism": (f"classes sharded x{world}" + (" + PGE pair rows sharded" if pge_sharded else ""))
+                   if world > 1 else "single GPU", "gemm_precision": ns.precision,
                    "l2": "inputs exceed L2: per epoch the PGE streams N'^2 x h fp32 activations (>800 MB at the "
                          "arxiv shape) and freshly sampled blocks through HBM; no explicit flush needed",
                    "sampled_block_bytes_per_epoch": int(sample_bytes_per_epoch)},

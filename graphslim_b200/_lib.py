@@ -61,6 +61,13 @@ SIGNATURES = {
                                          c_vp, c_vp, c_vp]),
     "gs_pge_bn1_bwd_reduce_f32": (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                           c_vp, c_vp, c_vp, c_vp]),
+    "gs_pge_l1_expand_rows_f32": (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gs_col_stats_partial_f64": (c_int, [c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "gs_col_stats_combine_f32": (c_int, [c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp]),
+    "gs_pge_bn1_bwd_work_bytes": (c_i64, [c_i32, c_i32]),
+    "gs_pge_bn1_bwd_pass_rows_f32": (c_int, [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                             c_i64, c_vp]),
+    "gs_pge_bn1_bwd_final_f32": (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gs_adam_step_f32": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_f64, c_f64, c_vp]),
     "gs_adam_table_f32": (c_int, [c_i32, c_f64, c_f64, c_f64, c_vp]),
     "gs_adam_step_table_f32": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64, c_f64, c_f64, c_vp]),

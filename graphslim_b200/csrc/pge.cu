@@ -139,8 +139,37 @@ __global__ void col_stats_final_kernel(int n, int h, const float* __restrict__ P
   rstd[idx] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// Column statistics of a row-sharded matrix from every rank's shifted partial sums (parallel-variance merge):
+// parts[r] = [S1 (h) | S2 (h) | shift (h)] with S1 = sum(y - shift), S2 = sum((y - shift)^2) over the rank's
+// counts[r] rows.  mean_r = shift + S1/n_r, M2_r = S2 - S1^2/n_r, then the usual merge in double.
+__global__ void col_stats_combine_kernel(int world, int h, const double* __restrict__ parts,
+                                         const int64_t* __restrict__ counts, float eps, float* __restrict__ mean,
+                                         float* __restrict__ rstd) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= h) return;
+  double n_tot = 0.0, mu = 0.0;
+  for (int r = 0; r < world; ++r) {
+    const double n_r = (double)counts[r];
+    const double* p = parts + (int64_t)r * 3 * h;
+    mu += n_r * (p[2 * h + k] + p[k] / n_r);
+    n_tot += n_r;
+  }
+  mu /= n_tot;
+  double m2 = 0.0;
+  for (int r = 0; r < world; ++r) {
+    const double n_r = (double)counts[r];
+    const double* p = parts + (int64_t)r * 3 * h;
+    const double mu_r = p[2 * h + k] + p[k] / n_r;
+    m2 += (p[h + k] - p[k] * p[k] / n_r) + n_r * (mu_r - mu) * (mu_r - mu);
+  }
+  double var = m2 / n_tot;
+  if (var < 0.0) var = 0.0;
+  mean[k] = (float)mu;
+  rstd[k] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
 // ------------------------------------------------------------------------------------------------
-__global__ void pge_l1_expand_kernel(int n, int h, const float* __restrict__ Pa, const float* __restrict__ Pb, Chunks ch,
+__global__ void pge_l1_expand_kernel(int n_i, int n, int h, const float* __restrict__ Pa, const float* __restrict__ Pb, Chunks ch,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float* __restrict__ H1) {
@@ -149,7 +178,7 @@ __global__ void pge_l1_expand_kernel(int n, int h, const float* __restrict__ Pa,
   const int k4 = threadIdx.x % h4;
   const int rsub = threadIdx.x / h4;
   if (rsub >= rows_per_pass) return;
-  const int64_t total = (int64_t)n * n;
+  const int64_t total = (int64_t)n_i * n;      // rows (i, j), i < n_i (a rank's slice of the first index), j < n
   const float4 g = reinterpret_cast<const float4*>(gamma)[k4];
   const float4 b = reinterpret_cast<const float4*>(beta)[k4];
   for (int64_t r = (int64_t)blockIdx.x * rows_per_pass + rsub; r < total; r += (int64_t)gridDim.x * rows_per_pass) {
@@ -536,14 +565,14 @@ pge_l3_fast_kernel(int64_t rows, const float* __restrict__ Y2, const float* __re
 // thread adds kB1I rows before it touches Ga (float4 atomics, L2 resident) and keeps its Gb partials in registers.
 constexpr int kB1I = 8;
 __global__ void __launch_bounds__(kRedThreads, 2)
-pge_bn1_bwd_pass_kernel(int n, int h, int jsplit, const float* __restrict__ dH1, const float* __restrict__ Pa,
+pge_bn1_bwd_pass_kernel(int n_i, int n, int h, int jsplit, const float* __restrict__ dH1, const float* __restrict__ Pa,
                         const float* __restrict__ Pb, const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ Ga,
                         float* __restrict__ Gb, double* __restrict__ tsum) {
   __shared__ __align__(16) float sm[2 * kRedThreads * 4];
   const RedLayout L = red_layout(h);
   const int i0 = blockIdx.x * kB1I;
-  const int ni = min(kB1I, n - i0);
+  const int ni = min(kB1I, n_i - i0);      // dH1, Pb and Gb are the caller's row slice: i counts from its first row
   const int per = (n + jsplit - 1) / jsplit;
   const int j0 = blockIdx.y * per, j1 = min(n, j0 + per);
   float4 acc[2] = {f4_zero(), f4_zero()};   // t1, t2
@@ -553,7 +582,7 @@ pge_bn1_bwd_pass_kernel(int n, int h, int jsplit, const float* __restrict__ dH1,
     float4 pb[kB1I], accB[kB1I];
 #pragma unroll
     for (int ii = 0; ii < kB1I; ++ii) {
-      pb[ii] = ld4(Pb + (int64_t)min(i0 + ii, n - 1) * h + k);
+      pb[ii] = ld4(Pb + (int64_t)min(i0 + ii, n_i - 1) * h + k);
       accB[ii] = f4_zero();
     }
     for (int j = j0 + L.lane_row; j < j1; j += L.rl) {
@@ -660,7 +689,7 @@ int gs_pge_bn1_bwd_closed_f32(int32_t n, int32_t h, const float* dH1, const floa
   int jsplit = (4 * kNumSMs + gx - 1) / gx;
   if (jsplit < 1) jsplit = 1;
   if (jsplit > n) jsplit = n;
-  pge_bn1_bwd_pass_kernel<<<dim3(gx, jsplit), kRedThreads, 0, st>>>(n, h, jsplit, dH1, Pa, Pb, mean, rstd, gamma, beta,
+  pge_bn1_bwd_pass_kernel<<<dim3(gx, jsplit), kRedThreads, 0, st>>>(n, n, h, jsplit, dH1, Pa, Pb, mean, rstd, gamma, beta,
                                                                    Ga, Gb, tsum);
   int rc = finish_launch("pge_bn1_bwd_pass");
   if (rc) return rc;
@@ -679,8 +708,78 @@ int gs_pge_l1_expand_f32(int32_t n, int32_t h, const float* Pa, const float* Pb,
   const int rpp = 256 / (h / 4);
   const int64_t want = ((int64_t)n * n + rpp - 1) / rpp;
   const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
-  pge_l1_expand_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, h, Pa, Pb, ch, mean, rstd, gamma, beta, H1);
+  pge_l1_expand_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, n, h, Pa, Pb, ch, mean, rstd, gamma, beta, H1);
   return finish_launch("pge_l1_expand");
+}
+
+// ---- row-sharded PGE (pair rows (i, j) with i in a rank's slice): the same kernels, reductions cut in two ----------
+int gs_pge_l1_expand_rows_f32(int32_t n_i, int32_t n, int32_t h, const float* Pa, const float* Pb_rows,
+                              const int64_t* chunk_off_rows, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, float* H1, void* stream) {
+  GS_REQUIRE(n_i > 0 && n > 0 && h > 0 && h % 4 == 0 && h / 4 <= 256 && Pa && Pb_rows && chunk_off_rows && mean && rstd &&
+             gamma && beta && H1);
+  Chunks ch{1, chunk_off_rows};
+  const int rpp = 256 / (h / 4);
+  const int64_t want = ((int64_t)n_i * n + rpp - 1) / rpp;
+  const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  pge_l1_expand_kernel<<<grid, 256, 0, as_stream(stream)>>>(n_i, n, h, Pa, Pb_rows, ch, mean, rstd, gamma, beta, H1);
+  return finish_launch("pge_l1_expand_rows");
+}
+
+int gs_col_stats_partial_f64(int64_t rows, int32_t h, const float* Y, const int64_t* chunk_off_rows, double* work,
+                             void* stream) {
+  GS_REQUIRE(rows > 0 && h > 0 && h % 4 == 0 && Y && chunk_off_rows && work);
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(work, 0, sizeof(double) * 2 * h, st);
+  Chunks ch{1, chunk_off_rows};
+  col_stats_partial_kernel<1><<<slice_grid(rows, 1), 256, 0, st>>>(1, h, nullptr, nullptr, Y, ch, work);
+  return finish_launch("col_stats_partial");
+}
+
+int gs_col_stats_combine_f32(int32_t world, int32_t h, const double* parts, const int64_t* counts, float eps,
+                             float* mean, float* rstd, void* stream) {
+  GS_REQUIRE(world > 0 && h > 0 && parts && counts && mean && rstd);
+  col_stats_combine_kernel<<<(h + 255) / 256, 256, 0, as_stream(stream)>>>(world, h, parts, counts, eps, mean, rstd);
+  return finish_launch("col_stats_combine");
+}
+
+int64_t gs_pge_bn1_bwd_work_bytes(int32_t n, int32_t h) {
+  return (int64_t)sizeof(double) * 2 * h + (int64_t)sizeof(float) * 2 * n * h;
+}
+
+int gs_pge_bn1_bwd_pass_rows_f32(int32_t n_i, int32_t i_first, int32_t n, int32_t h, const float* dH1_rows,
+                                 const float* Pa, const float* Pb, const float* mean, const float* rstd,
+                                 const float* gamma, const float* beta, void* work, int64_t work_bytes, void* stream) {
+  GS_REQUIRE(n_i > 0 && i_first >= 0 && i_first + n_i <= n && h > 0 && h % 4 == 0 && h <= 1024 && dH1_rows && Pa && Pb &&
+             mean && rstd && gamma && beta && work);
+  const int64_t need = gs_pge_bn1_bwd_work_bytes(n, h);
+  GS_REQUIRE(work_bytes >= need && (reinterpret_cast<uintptr_t>(work) & 15) == 0);
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(work, 0, (size_t)need, st);
+  double* tsum = reinterpret_cast<double*>(work);
+  float* Ga = reinterpret_cast<float*>(tsum + 2 * h);
+  float* Gb = Ga + (int64_t)n * h;
+  const int gx = (n_i + kB1I - 1) / kB1I;
+  int jsplit = (4 * kNumSMs + gx - 1) / gx;
+  if (jsplit < 1) jsplit = 1;
+  if (jsplit > n) jsplit = n;
+  pge_bn1_bwd_pass_kernel<<<dim3(gx, jsplit), kRedThreads, 0, st>>>(n_i, n, h, jsplit, dH1_rows,
+                                                                   Pa, Pb + (int64_t)i_first * h, mean, rstd, gamma, beta,
+                                                                   Ga, Gb + (int64_t)i_first * h, tsum);
+  return finish_launch("pge_bn1_bwd_pass_rows");
+}
+
+int gs_pge_bn1_bwd_final_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, const float* rstd,
+                             const float* gamma, const float* col_mean, const void* work, float* dPa, float* dPb,
+                             float* dgamma, float* dbeta, void* stream) {
+  GS_REQUIRE(n > 0 && h > 0 && Pa && Pb && rstd && gamma && col_mean && work && dPa && dPb && dgamma && dbeta);
+  const double* tsum = reinterpret_cast<const double*>(work);
+  const float* Ga = reinterpret_cast<const float*>(tsum + 2 * h);
+  const float* Gb = Ga + (int64_t)n * h;
+  const int64_t cnt = 2 * (int64_t)n * h;
+  pge_bn1_bwd_closed_final_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, as_stream(stream)>>>(
+      n, h, Pa, Pb, col_mean, rstd, gamma, Ga, Gb, tsum, dPa, dPb, dgamma, dbeta);
+  return finish_launch("pge_bn1_bwd_closed_final");
 }
 
 int gs_col_stats_chunked_f32(int64_t rows, int32_t h, const float* Y, int32_t nchunk, const int64_t* chunk_off,

@@ -387,6 +387,53 @@ class CudaOps:
                    "gs_pge_bn1_bwd_closed_f32")
         return dPa, dPb, dg, db
 
+    # ---- row-sharded PGE pieces (include/graphslim_b200.h, "row-sharded PGE") ----------------------------------
+    def pge_l1_expand_rows(self, Pa, Pb_rows, off_rows, mean, rstd, gamma, beta):
+        """H1 of the pair rows (i, j), i over the rows of `Pb_rows` (this rank's slice), j over all rows of Pa."""
+        n, h = Pa.shape
+        n_i = Pb_rows.shape[0]
+        H1 = self.empty(n_i * n, h)
+        _lib.check(self.lib.gs_pge_l1_expand_rows_f32(n_i, n, h, _ptr(Pa), _ptr(Pb_rows), _ptr(off_rows), _ptr(mean),
+                                                      _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(H1), self.stream),
+                   "gs_pge_l1_expand_rows_f32")
+        return H1
+
+    def col_stats_partial(self, Y, off_rows):
+        """float64 [sum(y - y[0]) | sum((y - y[0])^2)] over the rows of Y (2h)."""
+        rows, h = Y.shape
+        work = self._work(2 * h)
+        _lib.check(self.lib.gs_col_stats_partial_f64(rows, h, _ptr(Y), _ptr(off_rows), _ptr(work), self.stream),
+                   "gs_col_stats_partial_f64")
+        return work
+
+    def col_stats_combine(self, parts, counts, eps=1e-5):
+        """parts (world, 3h) float64 = per-rank [S1 | S2 | shift row]; counts (world,) int64 -> mean, rstd (1, h)."""
+        world, h3 = parts.shape
+        h = h3 // 3
+        mean, rstd = self.empty(1, h), self.empty(1, h)
+        _lib.check(self.lib.gs_col_stats_combine_f32(world, h, _ptr(parts), _ptr(counts), eps, _ptr(mean), _ptr(rstd),
+                                                     self.stream), "gs_col_stats_combine_f32")
+        return mean, rstd
+
+    def pge_bn1_bwd_pass_rows(self, dH1_rows, Pa, Pb, i_first, n_i, mean, rstd, gamma, beta):
+        """Linear reductions of dH1 over this rank's pair rows; returns the work buffer (float64 storage:
+        [t1, t2 (2h doubles) | Ga (n x h floats) | Gb (n x h floats)]) to be summed over the ranks."""
+        n, h = Pa.shape
+        nbytes = int(self.lib.gs_pge_bn1_bwd_work_bytes(n, h))
+        work = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gs_pge_bn1_bwd_pass_rows_f32(int(n_i), int(i_first), n, h, _ptr(dH1_rows), _ptr(Pa), _ptr(Pb),
+                                                         _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(work),
+                                                         work.numel() * 8, self.stream), "gs_pge_bn1_bwd_pass_rows_f32")
+        return work
+
+    def pge_bn1_bwd_final(self, Pa, Pb, rstd, gamma, col_mean, work):
+        n, h = Pa.shape
+        dPa, dPb, dg, db = self.empty(n, h), self.empty(n, h), self.empty(h), self.empty(h)
+        _lib.check(self.lib.gs_pge_bn1_bwd_final_f32(n, h, _ptr(Pa), _ptr(Pb), _ptr(rstd), _ptr(gamma), _ptr(col_mean),
+                                                     _ptr(work), _ptr(dPa), _ptr(dPb), _ptr(dg), _ptr(db), self.stream),
+                   "gs_pge_bn1_bwd_final_f32")
+        return dPa, dPb, dg, db
+
     def pge_l1_expand(self, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
         n, h = Pa.shape
         H1 = self.empty(n * n, h)

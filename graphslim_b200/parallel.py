@@ -3,8 +3,11 @@
 The matching loss is a sum of independent per-class terms (graphslim/condensation/gcond_base.py:210-239), so
 classes are dealt to ranks; every rank keeps a full replica of feat_syn / PGE / the condense model (same seed,
 same RNG streams) and computes d loss / d feat_syn and d loss / d A_hat for its classes only.  One all-reduce per
-outer step sums those partials (N'xd + N'xN' + 1 floats: 1-4 MB, latency-bound on NVLink); the PGE backward, the
-optimiser steps and the inner loop then run replicated and stay bit-identical across ranks.
+outer step sums those partials (N'xd + N'xN' + 1 floats: 1-4 MB, latency-bound on NVLink).  The adjacency generator
+(PGE) is sharded as well: its N'^2 pair rows are dealt to the ranks by slices of the first index, BatchNorm statistics
+and the linear backward reductions travel as small all-gathers / all-reduces, and the adjacency rows are all-gathered
+(pge.PGE.enable_row_sharding).  The optimiser steps and the inner loop run replicated and stay bit-identical across
+ranks.
 
 Index selection stays bit exact under sharding: every rank draws every class batch and replays the neighbour
 sampler's random stream, materialising only its own classes (csrc/host_sampler.cpp).
@@ -41,6 +44,30 @@ class _Sharded:
         self.owned_classes = self.class_partition[self.rank]
         if not self.owned_classes:
             raise ValueError(f"rank {self.rank} owns no class: world size {self.world} exceeds nclass {data.nclass}")
+        # the adjacency generator is the largest replicated piece: deal its N'^2 pair rows to the ranks too
+        self.pge_sharded = False
+        if getattr(self.args, "shard_pge", True) and not self.x_variant and getattr(self, "pge", None) is not None:
+            self.pge_sharded = self.pge.enable_row_sharding(group)
+
+    def sync_replicas(self):
+        """Rank 0's copy of everything the ranks update in lock step (synthetic features, PGE parameters, both Adam
+        states) is broadcast to the others.  The replicas compute the same updates from the same all-reduced
+        gradients, but products that accumulate split-K partials with atomics differ in their last bits from rank to
+        rank; one broadcast per epoch (a few MB) keeps that from compounding through Adam over hundreds of epochs."""
+        tensors = [self.feat_syn] + list(self.optimizer_feat.m) + list(self.optimizer_feat.v)
+        if not self.x_variant:
+            tensors += list(self.pge.parameters()) + list(self.optimizer_pge.m) + list(self.optimizer_pge.v)
+        flat = torch.cat([t.reshape(-1) for t in tensors])
+        dist.broadcast(flat, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        off = 0
+        for t in tensors:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+
+    def run_epoch(self, it):
+        super().run_epoch(it)
+        if self.world > 1:
+            self.sync_replicas()
 
     def reduce_partials(self, loss, dX, dA):
         parts = [loss.reshape(-1), dX.reshape(-1)] + ([dA.reshape(-1)] if dA is not None else [])

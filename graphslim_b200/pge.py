@@ -44,6 +44,97 @@ class PGE:
         self.chunk_off = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64, device=dev)
         self.eps = 1e-5
 
+    # ---------------------------------------------------------------------------------- row sharding
+    def enable_row_sharding(self, group=None):
+        """Deal the N'^2 pair rows (i, j) to the ranks of `group` by contiguous slices of i ("PGE's N'^2
+        pair rows can additionally be row-sharded with an allreduce of BN partial sums and an allgather of adjacency
+        rows").  Parameters stay replicated; every rank ends a forward with the full adjacency and a backward with the
+        full gradients, so the optimiser steps remain bit-identical across ranks.  The per-chunk BatchNorm of the
+        reddit >= 0.01 configuration is left replicated."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world == 1 or self.nchunks != 1 or self.n < world:
+            self.shard = None
+            return False
+        n, dev = self.n, self.K.device
+        bounds = [n * r // world for r in range(world + 1)]
+        rows = [(bounds[r + 1] - bounds[r]) * n for r in range(world)]
+        self.shard = dict(group=group, world=world, rank=rank, i0=bounds[rank], i1=bounds[rank + 1], bounds=bounds,
+                          rows=rows, pad=max(rows),
+                          off_rows=torch.tensor([0, rows[rank]], dtype=torch.int64, device=dev),
+                          counts=torch.tensor(rows, dtype=torch.int64, device=dev))
+        return True
+
+    def _forward_sharded(self, x, keep):
+        import torch.distributed as dist
+        K, n, d, h, sh = self.K, self.n, self.d, self.h, self.shard
+        W1 = self.W[0]
+        Pa = K.gemm(x, W1[:, :d], tb=True)
+        Pb = K.gemm(x, W1[:, d:], tb=True)
+        mean1, rstd1, cm1 = K.pge_l1_stats_closed(Pa, Pb, self.eps)            # 2n rows: replicated
+        H1 = K.pge_l1_expand_rows(Pa, Pb[sh["i0"]:sh["i1"]], sh["off_rows"], mean1, rstd1, self.gamma[0], self.beta[0])
+        with K.timed("pge_l2_fwd"):
+            Y2 = K.gemm(H1, self.W[1], tb=True)
+        part = torch.cat([K.col_stats_partial(Y2, sh["off_rows"]), Y2[0].double()])
+        parts = torch.empty(sh["world"] * 3 * h, dtype=torch.float64, device=K.device)
+        dist.all_gather_into_tensor(parts, part, group=sh["group"])            # BN2 partial sums: 3h doubles per rank
+        mean2, rstd2 = K.col_stats_combine(parts.view(sh["world"], 3 * h), sh["counts"], self.eps)
+        E_loc = K.pge_l3(Y2, sh["off_rows"], mean2, rstd2, self.gamma[1], self.beta[1], self.W[2].view(-1), self.b[2])
+        send = E_loc
+        if E_loc.numel() != sh["pad"]:
+            send = torch.zeros(sh["pad"], dtype=torch.float32, device=K.device)
+            send[:E_loc.numel()] = E_loc
+        full = torch.empty(sh["world"] * sh["pad"], dtype=torch.float32, device=K.device)
+        dist.all_gather_into_tensor(full, send, group=sh["group"])             # adjacency rows of every rank
+        if all(r == sh["pad"] for r in sh["rows"]):
+            E = full
+        else:
+            E = torch.cat([full[r * sh["pad"]: r * sh["pad"] + sh["rows"][r]] for r in range(sh["world"])])
+        A = K.pge_symm_sigmoid(E, n)
+        if keep:
+            self._saved = (x, Pa, Pb, mean1, rstd1, cm1, H1, Y2, mean2, rstd2, A)
+        return A
+
+    def _backward_sharded(self, dA):
+        import torch.distributed as dist
+        K, n, d, h, sh = self.K, self.n, self.d, self.h, self.shard
+        x, Pa, Pb, mean1, rstd1, cm1, H1, Y2, mean2, rstd2, A = self._saved
+        W1, W2, w3 = self.W[0], self.W[1], self.W[2].view(-1)
+        grp = sh["group"]
+        dE = K.pge_symm_sigmoid_bwd(dA, A)
+        dE_loc = dE[sh["i0"] * n: sh["i1"] * n]
+        s1, s2, dw3, db3 = K.pge_l3_bwd_stats(Y2, dE_loc, sh["off_rows"], mean2, rstd2, self.gamma[1], self.beta[1], w3)
+        flat = torch.cat([s1.view(-1), s2.view(-1), dw3.view(-1), db3.view(-1)])
+        dist.all_reduce(flat, group=grp)                                       # BN2 backward sums + layer-3 grads
+        s1, s2, dw3, db3 = flat[:h].view(1, h), flat[h:2 * h].view(1, h), flat[2 * h:3 * h], flat[3 * h:3 * h + 1]
+        dgamma2, dbeta2 = s2.sum(0), s1.sum(0)
+        # the apply kernel divides the sums by the row count of the rows it is given: pre-scale to the global count
+        scale = float(sh["rows"][sh["rank"]]) / float(n * n)
+        dY2 = K.pge_bn2_bwd_apply(Y2, dE_loc, sh["off_rows"], mean2, rstd2, self.gamma[1], self.beta[1], w3,
+                                  s1 * scale, s2 * scale)
+        with K.timed("pge_l2_bwd_dw"):
+            dW2 = K.gemm(dY2, H1, ta=True)
+        with K.timed("pge_l2_bwd_dx"):
+            dH1 = K.gemm(dY2, W2)
+        work = K.pge_bn1_bwd_pass_rows(dH1, Pa, Pb, sh["i0"], sh["i1"] - sh["i0"], mean1, rstd1, self.gamma[0],
+                                       self.beta[0])
+        dist.all_reduce(work[:2 * h], group=grp)                               # t1, t2 (float64)
+        red = torch.cat([work[2 * h:].view(torch.float32), dW2.view(-1)])
+        dist.all_reduce(red, group=grp)                                        # Ga, Gb and dW2 (float32)
+        nfl = 2 * n * h
+        work[2 * h:].view(torch.float32).copy_(red[:nfl])
+        dW2 = red[nfl:].view(h, h)
+        dPa, dPb, dgamma1, dbeta1 = K.pge_bn1_bwd_final(Pa, Pb, rstd1, self.gamma[0], cm1, work)
+        dW1 = K.empty(h, 2 * d)
+        K.gemm(dPa, x, ta=True, out=dW1[:, :d])
+        K.gemm(dPb, x, ta=True, out=dW1[:, d:])
+        dX = K.gemm(dPa, W1[:, :d])
+        K.gemm(dPb, W1[:, d:], out=dX, beta=1.0)
+        zeros_h = K.zeros(h)
+        grads = [dW1, zeros_h, dW2, zeros_h.clone(), dw3.reshape(1, h), db3.reshape(1), dgamma1, dbeta1, dgamma2, dbeta2]
+        self._saved = None
+        return grads, dX
+
     def parameters(self):
         return [self.W[0], self.b[0], self.W[1], self.b[1], self.W[2], self.b[2],
                 self.gamma[0], self.beta[0], self.gamma[1], self.beta[1]]
@@ -51,6 +142,8 @@ class PGE:
     # ---------------------------------------------------------------------------------- forward
     def forward(self, x, keep=True):
         """adj (n,n) = zero-diag(sigmoid((E+E^T)/2)),  E[i,j] = MLP([x_j, x_i]).  BN always uses batch stats."""
+        if getattr(self, "shard", None) is not None:
+            return self._forward_sharded(x, keep)
         K, n, d, h = self.K, self.n, self.d, self.h
         W1 = self.W[0]
         Pa = K.gemm(x, W1[:, :d], tb=True)                       # layer 1, first half: indexed by j
@@ -80,6 +173,8 @@ class PGE:
     # ---------------------------------------------------------------------------------- backward
     def backward(self, dA):
         """Returns (grads in parameters() order, dX)."""
+        if getattr(self, "shard", None) is not None:
+            return self._backward_sharded(dA)
         K, n, d, h = self.K, self.n, self.d, self.h
         x, Pa, Pb, mean1, rstd1, cm1, H1, Y2, mean2, rstd2, A = self._saved
         W1, W2, w3 = self.W[0], self.W[1], self.W[2].view(-1)

@@ -217,6 +217,30 @@ int gs_pge_bn1_bwd_reduce_f32(int32_t n, int32_t h, const float* dH1, const floa
                               const float* beta, const float* s1, const float* s2, float* dPa, float* dPb,
                               void* stream);
 
+/* ---- row-sharded PGE (one box, pair rows (i, j) with i in this rank's slice; graphslim_b200/pge.py ShardedPGE).
+ * The kernels are the ones above; every reduction over all N'^2 pair rows is cut into a per-rank partial and a
+ * replicated combine with one small collective in between (no reference counterpart: the reference is single-GPU).
+ *   gs_pge_l1_expand_rows_f32     H1 rows of the slice: n_i x n pair rows from Pa (all j) and Pb_rows (the slice's i)
+ *   gs_col_stats_partial_f64      work[0..h) = sum(y - y_row0), work[h..2h) = sum((y - y_row0)^2) over the slice
+ *   gs_col_stats_combine_f32      parts[world][3h] = (S1 | S2 | shift row) + counts[world] -> mean, rstd over all rows
+ *   gs_pge_bn1_bwd_pass_rows_f32  linear reductions of dH1 over the slice into work = [t1,t2 (2h doubles) | Ga (n x h) |
+ *                                 Gb (n x h, only the slice's rows non-zero)]; summed over ranks by the caller
+ *   gs_pge_bn1_bwd_final_f32      dPa, dPb, dgamma1, dbeta1 from the summed work */
+int gs_pge_l1_expand_rows_f32(int32_t n_i, int32_t n, int32_t h, const float* Pa, const float* Pb_rows,
+                              const int64_t* chunk_off_rows, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, float* H1, void* stream);
+int gs_col_stats_partial_f64(int64_t rows, int32_t h, const float* Y, const int64_t* chunk_off_rows, double* work,
+                             void* stream);
+int gs_col_stats_combine_f32(int32_t world, int32_t h, const double* parts, const int64_t* counts, float eps,
+                             float* mean, float* rstd, void* stream);
+int64_t gs_pge_bn1_bwd_work_bytes(int32_t n, int32_t h);
+int gs_pge_bn1_bwd_pass_rows_f32(int32_t n_i, int32_t i_first, int32_t n, int32_t h, const float* dH1_rows,
+                                 const float* Pa, const float* Pb, const float* mean, const float* rstd,
+                                 const float* gamma, const float* beta, void* work, int64_t work_bytes, void* stream);
+int gs_pge_bn1_bwd_final_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, const float* rstd,
+                             const float* gamma, const float* col_mean, const void* work, float* dPa, float* dPb,
+                             float* dgamma, float* dbeta, void* stream);
+
 /* ---- optimiser (torch.optim.Adam defaults; condensation/gcond_base.py:68-69, gcond.py:44) ---- */
 int gs_adam_step_f32(int64_t n, float* p, const float* g, float* m, float* v, int32_t step, double lr, double beta1,
                      double beta2, double eps, void* stream);

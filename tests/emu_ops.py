@@ -244,6 +244,54 @@ class EmuOps:
         dPa, dPb = self.pge_bn1_bwd_reduce(dH1, Pa, Pb, off, mean, rstd, gamma, beta, s1, s2)
         return dPa, dPb, s2.sum(0), s1.sum(0)
 
+    # ---- row-sharded PGE pieces (same contracts as CudaOps)
+    def pge_l1_expand_rows(self, Pa, Pb_rows, off_rows, mean, rstd, gamma, beta):
+        n, h = Pa.shape
+        y = (Pb_rows[:, None, :] + Pa[None, :, :]).reshape(-1, h)
+        return torch.relu(gamma * ((y - mean) * rstd) + beta)
+
+    def col_stats_partial(self, Y, off_rows):
+        y = Y.double() - Y[0].double()
+        return torch.cat([y.sum(0), (y * y).sum(0)])
+
+    def col_stats_combine(self, parts, counts, eps=1e-5):
+        h = parts.shape[1] // 3
+        n_r = counts.double()[:, None]
+        S1, S2, shift = parts[:, :h], parts[:, h:2 * h], parts[:, 2 * h:]
+        mu_r = shift + S1 / n_r
+        mu = (n_r * mu_r).sum(0) / n_r.sum()
+        m2 = ((S2 - S1 * S1 / n_r) + n_r * (mu_r - mu) ** 2).sum(0)
+        var = (m2 / n_r.sum()).clamp_(min=0)
+        return mu.float().view(1, -1), (1.0 / torch.sqrt(var + eps)).float().view(1, -1)
+
+    def pge_bn1_bwd_pass_rows(self, dH1_rows, Pa, Pb, i_first, n_i, mean, rstd, gamma, beta):
+        n, h = Pa.shape
+        y = (Pb[i_first:i_first + n_i, None, :] + Pa[None, :, :])                 # (n_i, n, h)
+        xh = (y - mean.view(1, 1, h)) * rstd.view(1, 1, h)
+        g = dH1_rows.view(n_i, n, h) * ((gamma * xh + beta) > 0)
+        work = torch.zeros(2 * h + n * h, dtype=torch.float64)
+        work[:h] = g.double().sum((0, 1))
+        work[h:2 * h] = (g.double() * xh.double()).sum((0, 1))
+        fl = work[2 * h:].view(torch.float32)
+        fl[:n * h] = g.sum(0).reshape(-1)                                         # Ga[j]
+        Gb = torch.zeros(n, h)
+        Gb[i_first:i_first + n_i] = g.sum(1)
+        fl[n * h:] = Gb.reshape(-1)
+        return work
+
+    def pge_bn1_bwd_final(self, Pa, Pb, rstd, gamma, col_mean, work):
+        n, h = Pa.shape
+        tsum = work[:2 * h]
+        fl = work[2 * h:].view(torch.float32)
+        Ga, Gb = fl[:n * h].view(n, h), fl[n * h:].view(n, h)
+        m = float(n) * float(n)
+        a1n = (tsum[:h] * n / m).float()
+        a2 = (tsum[h:] / m).float()
+        rs = rstd.view(-1)
+        dPa = gamma * rs * (Ga - a1n - rs * n * (Pa - col_mean[0]) * a2)
+        dPb = gamma * rs * (Gb - a1n - rs * n * (Pb - col_mean[1]) * a2)
+        return dPa, dPb, tsum[h:].float(), tsum[:h].float()
+
     def pge_l1_expand(self, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
         y = self._y1(Pa, Pb)
         rows = y.shape[0]

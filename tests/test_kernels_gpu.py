@@ -327,6 +327,49 @@ def test_adam_matches_torch(K):
 
 
 # ------------------------------------------------------------------------------------------ PGE kernels
+@pytest.mark.parametrize("n,h,cuts", [(37, 128, [0, 12, 37]), (64, 256, [0, 16, 32, 48, 64]), (70, 128, [0, 23, 46, 70])])
+def test_pge_row_sharded_pieces_match_unsharded(K, n, h, cuts):
+    """The per-rank halves of the row-sharded PGE (expand rows, partial / combined BatchNorm statistics, BN1 backward
+    pass / final) reproduce the unsharded kernels when the slices are combined the way the collectives combine them."""
+    gen = torch.Generator().manual_seed(n * h)
+    dev = "cuda"
+    Pa = torch.randn(n, h, generator=gen).to(dev)
+    Pb = (torch.randn(n, h, generator=gen) + 0.5).to(dev)
+    gamma = (torch.rand(h, generator=gen) + 0.5).to(dev)
+    beta = (torch.randn(h, generator=gen) * 0.1).to(dev)
+    off = torch.tensor([0, n * n], dtype=torch.int64, device=dev)
+    offs = [torch.tensor([0, (b - a) * n], dtype=torch.int64, device=dev) for a, b in zip(cuts[:-1], cuts[1:])]
+    mean1, rstd1, cm1 = K.pge_l1_stats_closed(Pa, Pb)
+    # layer-1 expansion: bit-identical rows
+    H1 = K.pge_l1_expand(Pa, Pb, off, mean1, rstd1, gamma, beta)
+    H1s = torch.cat([K.pge_l1_expand_rows(Pa, Pb[a:b], o, mean1, rstd1, gamma, beta)
+                     for (a, b), o in zip(zip(cuts[:-1], cuts[1:]), offs)])
+    assert torch.equal(H1, H1s)
+    # column statistics: shifted partial sums merged in double
+    Y = (torch.randn(n * n, h, generator=gen) * 3 + 1).to(dev)
+    mean, rstd = K.col_stats_chunked(Y, off)
+    parts = torch.stack([torch.cat([K.col_stats_partial(Y[a * n:b * n], o), Y[a * n].double()])
+                         for (a, b), o in zip(zip(cuts[:-1], cuts[1:]), offs)])
+    counts = torch.tensor([(b - a) * n for a, b in zip(cuts[:-1], cuts[1:])], dtype=torch.int64, device=dev)
+    mean_s, rstd_s = K.col_stats_combine(parts, counts)
+    close(mean_s, mean, rtol=1e-6)
+    close(rstd_s, rstd, rtol=1e-5)
+    # BN1 backward: per-slice linear reductions, summed like the all-reduce does
+    dH1 = torch.randn(n * n, h, generator=gen).to(dev)
+    ref = K.pge_bn1_bwd_closed(dH1, Pa, Pb, mean1, rstd1, gamma, beta, cm1)
+    work = None
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        w = K.pge_bn1_bwd_pass_rows(dH1[a * n:b * n], Pa, Pb, a, b - a, mean1, rstd1, gamma, beta)
+        if work is None:
+            work = w
+        else:
+            work[:2 * h] += w[:2 * h]
+            work[2 * h:].view(torch.float32).add_(w[2 * h:].view(torch.float32))
+    got = K.pge_bn1_bwd_final(Pa, Pb, rstd1, gamma, cm1, work)
+    for g_, r_ in zip(got, ref):
+        close(g_, r_, rtol=1e-4)
+
+
 @pytest.mark.parametrize("n,h,nchunk", [(70, 128, 1), (40, 128, 5), (153, 256, 1), (97, 128, 5)])
 def test_pge_kernels(K, E, n, h, nchunk):
     gen = torch.Generator().manual_seed(n + h + nchunk)

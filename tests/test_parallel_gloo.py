@@ -34,15 +34,19 @@ def _worker(rank, world, port, name, out_dir):
     agent.trace = lambda kind, **kw: losses.append(float(kw["loss"].item())) if kind == "grads" else None
     agent.reduce(data, verbose=False)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), losses=np.array(losses), feat=agent.feat_syn.numpy(),
-             owned=np.array(agent.owned_classes), pge=np.concatenate([p.numpy().ravel() for p in agent.pge.parameters()]))
+             owned=np.array(agent.owned_classes), pge=np.concatenate([p.numpy().ravel() for p in agent.pge.parameters()]),
+             pge_sharded=np.array(bool(getattr(agent, "pge_sharded", False))))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["mini_sgc2_arxiv", "mini_gcn_flickr"])
-def test_two_rank_class_sharding_matches_single_process(name, tmp_path):
+@pytest.mark.parametrize("name,world", [("mini_sgc2_arxiv", 2), ("mini_gcn_flickr", 2), ("mini_sgc2_arxiv", 3)])
+def test_class_and_pge_sharding_matches_single_process(name, world, tmp_path):
+    """Classes dealt to the ranks AND the PGE pair rows dealt to the ranks (uneven slices at world 3: N' = 40)."""
     port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, name, str(tmp_path)), nprocs=2, join=True)
-    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    mp.spawn(_worker, args=(world, port, name, str(tmp_path)), nprocs=world, join=True)
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    r0, r1 = ranks[0], ranks[-1]
+    assert all(bool(r["pge_sharded"]) for r in ranks)
     assert set(r0["owned"]).isdisjoint(set(r1["owned"]))
     # replicas stay identical
     assert np.array_equal(r0["feat"], r1["feat"]) and np.array_equal(r0["pge"], r1["pge"])

@@ -100,16 +100,25 @@ class InnerLoop:
             self._one_step()               # first step runs eagerly: lazily configured kernels, workspace growth
             self.warm = True
             return
+        # capture_begin/capture_end directly: the torch.cuda.graph() context manager also empties the caching
+        # allocator, which would hand the ~GB PGE activations back to the driver in the middle of a run
         graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(self.K.device)
+        side.wait_stream(torch.cuda.current_stream(self.K.device))
         try:
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                self._one_step()
+            with torch.cuda.stream(side):
+                graph.capture_begin(capture_error_mode="thread_local")
+                try:
+                    self._one_step()
+                finally:
+                    graph.capture_end()
         except Exception as exc:           # stay correct on anything the capture cannot express
             self.use_graph = False
             self.capture_error = repr(exc)
             torch.cuda.synchronize(self.K.device)
             self._one_step()
             return
+        torch.cuda.current_stream(self.K.device).wait_stream(side)
         self.graph = graph
         self.graph.replay()                # capture does not execute: run the step it recorded
         self.replays += 1

@@ -371,6 +371,7 @@ def run_ours(ns):
     h2d = graph_bytes / K_ + getattr(e2e_agent.sampler, "bytes_moved", 0) / K_
     d2h = (feat_host.numel() + adj_host.numel()) * 4 / K_
     e2e = {"value": K_ / e2e_s, "unit": "epochs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "seconds_total": e2e_s, "seconds_setup_host": getattr(e2e_agent, "setup_seconds", None),
            "note": "GCond(...).reduce(data) on host tensors: graph+features H2D, normalisation, init, K epochs "
                    "(each streaming sampled blocks H2D), result D2H; one-off setup amortised over K epochs"}
 

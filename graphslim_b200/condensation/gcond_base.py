@@ -304,17 +304,16 @@ class GCondBase:
 
     # ------------------------------------------------------------------ checkpoint hook (gcond_base.py:287-324)
     def intermediate_evaluation(self, best_val, loss_avg=None, save=True):
-        """The reference trains an evaluation GCN here (SURVEY section 8f, next scope).  An evaluator can be plugged
-        in as ``args.evaluator(data, args) -> (val, test)``; without one the condensed graph is saved as is."""
+        """gcond_base.py:287-324: `run_inter_eval` runs of test_with_val on the published condensed graph; the graph is
+        saved when the mean validation accuracy improves.  ``args.evaluator(data, args) -> (val, test)`` replaces the
+        built-in GCN evaluator (graphslim_b200/evaluation.py) when given."""
         from ..dataset_utils import save_reduced
         data, args = self.data, self.args
         if args.verbose:
             print('loss_avg: {}'.format(loss_avg))
         evaluator = getattr(args, "evaluator", None)
         if evaluator is None:
-            if save:
-                save_reduced(data.adj_syn, data.feat_syn, data.labels_syn, args)
-            return best_val
+            evaluator = lambda d, a: self.test_with_val(setting=a.setting, iters=a.eval_epochs)
         res = np.array([evaluator(data, args) for _ in range(args.run_inter_eval)]).T
         current_val = res[0].mean()
         args.logger.info('\nVal:  {:.4f} +/- {:.4f}'.format(100 * current_val, 100 * res[0].std()))
@@ -323,3 +322,11 @@ class GCondBase:
             best_val = current_val
             save_reduced(data.adj_syn, data.feat_syn, data.labels_syn, args)
         return best_val
+
+    def test_with_val(self, verbose=False, setting='trans', iters=200, best_val=None):
+        """gcond_base.py:326-358 -> [validation accuracy, test accuracy] of a fresh eval GCN trained on the condensed
+        graph (full-graph validation forward every iteration)."""
+        from ..evaluation import GCNEvaluator
+        if getattr(self, "_evaluator", None) is None:
+            self._evaluator = GCNEvaluator(self.K, self.data, self.args)
+        return self._evaluator.test_with_val(iters=iters, setting=setting)

@@ -1,0 +1,70 @@
+"""Checkpoint evaluator (graphslim_b200/evaluation.py) against fixtures produced by the UNMODIFIED reference's
+GCondBase.test_with_val (oracle/make_eval_goldens.py): same condensed graph, same generator state.
+
+* the eval model's initial parameters are bit-exact (torch CPU generator, constructor draw + initialize());
+* the validation accuracy after each of the first training iterations and the best validation / test accuracies agree
+  to within a few validation nodes (fp32 reassociation flips an argmax here and there).
+
+CPU: kernels replaced by their PyTorch references (tests/emu_ops.py).  GPU: the CUDA path through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.cases import GOLDEN_DIR
+from tests import helpers
+
+CASES = ["mini_sgc2_arxiv", "mini_gcn_flickr"]
+
+
+def _run(name, K, device):
+    from graphslim_b200 import data as gdata
+    from graphslim_b200.evaluation import GCNEvaluator
+    gold = np.load(os.path.join(GOLDEN_DIR, f"eval_{name}.npz"))
+    args = helpers.case_args(name, device=device, save_init=False, progress=False)
+    args.eval_epochs = int(gold["iters"])
+    raw = helpers.case_graph(name)
+    data = gdata.TransAndInd(raw, args.dataset, args.pre_norm)
+    data.adj_syn = torch.from_numpy(gold["adj_syn"])
+    data.feat_syn = torch.from_numpy(gold["feat_syn"])
+    data.labels_syn = torch.from_numpy(gold["labels_syn"])
+    ev = GCNEvaluator(K, data, args)
+    helpers.seed_everything(args.seed + 17)
+    out = []
+    for run in range(gold["res"].shape[0]):
+        res = ev.test_with_val()
+        init = np.concatenate([w.cpu().numpy().ravel() for w in ev.last_init])
+        out.append((res, init, np.array(ev.last_val_curve)))
+    probe = torch.randint(0, 2**31 - 1, (4,)).numpy()
+    return gold, out, probe, data
+
+
+def _check(gold, out, probe, data):
+    n_val = len(np.asarray(data.labels_val))
+    n_test = len(np.asarray(data.labels_test))
+    for run, (res, init, curve) in enumerate(out):
+        np.testing.assert_array_equal(init, gold["model_init"][run])          # parameter draws: bit exact
+        ref_curve = gold["val_curve"][run]
+        assert curve.shape == ref_curve.shape
+        # early iterations: identical state, only fp32 reassociation -> at most a couple of validation nodes apart
+        assert np.abs(curve[:10] - ref_curve[:10]).max() <= 3.0 / n_val + 1e-12
+        # whole trajectory: bounded drift
+        assert np.abs(curve - ref_curve).max() <= 0.05
+        assert abs(res[0] - gold["res"][run, 0]) <= 3.0 / n_val + 1e-12       # best validation accuracy
+        assert abs(res[1] - gold["res"][run, 1]) <= 0.05 + 3.0 / n_test       # test accuracy of the selected model
+    np.testing.assert_array_equal(probe, gold["torch_rng_probe"])             # total generator consumption
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_evaluator_emulated_matches_reference_fixture(name):
+    from tests.emu_ops import EmuOps
+    _check(*_run(name, EmuOps("cpu"), "cpu"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("name", CASES)
+def test_evaluator_cuda_matches_reference_fixture(name, precision):
+    from graphslim_b200.ops import CudaOps
+    _check(*_run(name, CudaOps("cuda:0", precision=precision), "cuda"))

@@ -190,9 +190,11 @@ int gs_gemm_epi_f32(int ta, int tb, int32_t M, int32_t N, int32_t K, float alpha
   // the complete sum in one thread, so those products stay unsplit
   const int64_t tiles = (int64_t)((M + 63) / 64) * ((N + 63) / 64);
   int splits = 1;
-  if (K >= 2048 && tiles < 2 * gs::kNumSMs && !epi) {
+  // (K >= 512: the 70 x 1433 x 7 logits product of the Cora-shape inner loop ran 238 us as one serial K loop on two
+  // CTAs -- 70 % of an inner step; profiles/r1_gemm_shapes_cora.json)
+  if (K >= 512 && tiles < 2 * gs::kNumSMs && !epi) {
     splits = (int)((2 * gs::kNumSMs + tiles - 1) / tiles);
-    const int max_splits = (K + 511) / 512;
+    const int max_splits = K >= 2048 ? (K + 511) / 512 : (K + 127) / 128;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }

@@ -68,3 +68,36 @@ def test_evaluator_emulated_matches_reference_fixture(name):
 def test_evaluator_cuda_matches_reference_fixture(name, precision):
     from graphslim_b200.ops import CudaOps
     _check(*_run(name, CudaOps("cuda:0", precision=precision), "cuda"))
+
+
+def test_reduce_with_checkpoints_runs_the_builtin_evaluator(tmp_path, monkeypatch):
+    """GCond.reduce with a checkpoint epoch: the published condensed graph goes through intermediate_evaluation
+    (run_inter_eval runs of the built-in GCN evaluator) and is saved in the reference's three-file format when the
+    validation accuracy improves (gcond.py:75-78, gcond_base.py:287-324, dataset/utils.py:136-152)."""
+    import logging
+    from graphslim_b200 import data as gdata
+    from graphslim_b200.condensation import gcond_base
+    from graphslim_b200.reduction import create_reducer
+    from tests.emu_ops import EmuOps
+    monkeypatch.setattr(gcond_base, "_kernels", lambda device, args: EmuOps(device))
+    name = "mini_sgc2_arxiv"
+    args = helpers.case_args(name, save_init=False, progress=False, save_path=str(tmp_path))
+    args.epochs, args.checkpoints, args.eval_epochs, args.run_inter_eval = 3, [1], 8, 2
+    records = []
+    handler = logging.Handler()
+    handler.emit = lambda rec: records.append(rec.getMessage())
+    args.logger.addHandler(handler)
+    args.logger.setLevel(logging.INFO)
+    raw = helpers.case_graph(name)
+    helpers.seed_everything(args.seed)
+    data = gdata.TransAndInd(raw, args.dataset, args.pre_norm)
+    agent = create_reducer(args.method, setting=args.setting, data=data, args=args)
+    try:
+        agent.reduce(data, verbose=False)
+    finally:
+        args.logger.removeHandler(handler)
+    assert 0.0 < agent.best_val <= 1.0
+    assert any(m.strip().startswith("Val:") for m in records) and any(m.startswith("Test:") for m in records)
+    saved = [f for _, _, fs in os.walk(tmp_path) for f in fs if f.endswith(".pt")]
+    assert any(f.startswith("adj_") for f in saved) and any(f.startswith("feat_") for f in saved) and \
+        any(f.startswith("label_") for f in saved)

@@ -6,7 +6,7 @@ from tqdm import trange
 
 from .. import engine as _engine
 from ..dataset_utils import verbose_time_memory
-from .gcond_base import GCondBase, InnerLoop
+from .gcond_base import GCondBase, InnerLoop, MatchGraph
 
 
 class GCond(GCondBase):
@@ -41,6 +41,8 @@ class GCond(GCondBase):
         # traced runs (parity tests read intermediate tensors) stay on the step-by-step path
         self.inner = InnerLoop(K, self.model, self.feat_syn, self.nnodes_syn, args.lr, outer_loop * inner_loop,
                                use_graph=getattr(args, "cuda_graphs", True) and self.trace is None)
+        self.match_graph = MatchGraph(K, self.model, self.feat_syn, args.dis_metric,
+                                      use_graph=getattr(args, "cuda_graphs", True) and self.trace is None)
         self.loss_avg, self.best_val = 0, 0
         self.adj_syn_inner = None
         self._pge_ready = None

@@ -100,28 +100,82 @@ class InnerLoop:
             self._one_step()               # first step runs eagerly: lazily configured kernels, workspace growth
             self.warm = True
             return
-        # capture_begin/capture_end directly: the torch.cuda.graph() context manager also empties the caching
-        # allocator, which would hand the ~GB PGE activations back to the driver in the middle of a run
         graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(self.K.device)
-        side.wait_stream(torch.cuda.current_stream(self.K.device))
         try:
-            with torch.cuda.stream(side):
-                graph.capture_begin(capture_error_mode="thread_local")
-                try:
-                    self._one_step()
-                finally:
-                    graph.capture_end()
+            _capture(self.K, graph, self._one_step)
         except Exception as exc:           # stay correct on anything the capture cannot express
             self.use_graph = False
             self.capture_error = repr(exc)
             torch.cuda.synchronize(self.K.device)
             self._one_step()
             return
-        torch.cuda.current_stream(self.K.device).wait_stream(side)
         self.graph = graph
         self.graph.replay()                # capture does not execute: run the step it recorded
         self.replays += 1
+
+
+def _capture(K, graph, body):
+    """Capture `body()` into `graph` on a side stream (capture_begin/capture_end directly: the torch.cuda.graph()
+    context manager also empties the caching allocator, which would hand the ~GB PGE activations back to the driver in
+    the middle of a run).  Returns body's result; raises whatever the capture raised."""
+    side = torch.cuda.Stream(K.device)
+    side.wait_stream(torch.cuda.current_stream(K.device))
+    with torch.cuda.stream(side):
+        graph.capture_begin(capture_error_mode="thread_local")
+        try:
+            out = body()
+        finally:
+            graph.capture_end()
+    torch.cuda.current_stream(K.device).wait_stream(side)
+    return out
+
+
+class MatchGraph:
+    """The fixed-shape middle of an outer step -- synthetic forward, first-order gradients, matching distance and the
+    second-order backward (gcond_base.py:210-239 for all classes at once, ~90 small launches) -- captured once in a CUDA
+    graph and replayed.  Inputs that are fresh tensors every step (the real-side class-column gradients, the normalised
+    adjacency) are copied into fixed buffers first; loss, dX and dA come back in the graph's own fixed outputs, which
+    the caller consumes before the next replay.  First call eager (lazy kernel configuration, workspace growth), second
+    call captures, later calls replay; a failed capture falls back to the step-by-step path for good."""
+
+    def __init__(self, K, model, feat_syn, metric, use_graph=True):
+        self.K, self.model, self.feat, self.metric = K, model, feat_syn, metric
+        self.use_graph = bool(use_graph) and torch.device(K.device).type == "cuda"
+        self.graph, self.calls, self.replays = None, 0, 0
+        self.gr = self.adj = self.out = None
+
+    def _body(self, gr, adj, need_dA):
+        K, model = self.K, self.model
+        model.syn_forward(self.feat, adj)
+        gs = model.syn_grads()
+        loss = K.zeros(1)
+        G = K.match(gs, gr, model.widths, model.is_bias, model.lay.coeff, self.metric, loss)
+        dX, dA = model.syn_backward(G, need_dA=need_dA)
+        return loss, dX, dA
+
+    def run(self, gr, adj, need_dA):
+        self.calls += 1
+        if not self.use_graph or self.calls == 1:
+            return self._body(gr, adj, need_dA)
+        if self.graph is None:
+            self.gr = [g.clone() for g in gr]
+            self.adj = adj.clone()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                self.out = _capture(self.K, graph, lambda: self._body(self.gr, self.adj, need_dA))
+            except Exception as exc:
+                self.use_graph, self.capture_error = False, repr(exc)
+                torch.cuda.synchronize(self.K.device)
+                return self._body(gr, adj, need_dA)
+            self.graph = graph
+        else:
+            for dst, src in zip(self.gr, gr):
+                dst.copy_(src)
+            if adj.data_ptr() != self.adj.data_ptr():
+                self.adj.copy_(adj)
+        self.graph.replay()
+        self.replays += 1
+        return self.out
 
 
 class GCondBase:
@@ -273,6 +327,11 @@ class GCondBase:
             self.trace("sample", rb=rb)
         with K.timed("phase_real_grads"):
             gr = model.real_grads(rb, self.features, self.ones_full, self.features_padded)
+        mg = getattr(self, "match_graph", None)
+        if mg is not None and mg.use_graph and self.trace is None:
+            with K.timed("phase_syn_graph"):                 # forward + gradients + matching + backward, one replay
+                loss, dX, dA = mg.run(gr, self.adj_syn, not model.identity_adj)
+            return loss, dX, dA, rb
         with K.timed("phase_syn_forward_grads"):
             model.syn_forward(self.feat_syn, self.adj_syn)
             gs = model.syn_grads()

@@ -169,6 +169,9 @@ class CudaOps:
         makes reuse safe: the next pack kernel runs after the previous GEMM has finished reading)."""
         ws = getattr(self, "_ws", None)
         if ws is None or ws.numel() < nbytes:
+            if ws is not None:
+                # captured CUDA graphs (inner loop, matching segment) hold this buffer's address: keep it alive
+                self.__dict__.setdefault("_ws_retired", []).append(ws)
             ws = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, device=self.device)
             self._ws = ws
         return ws

@@ -87,8 +87,10 @@ def test_inner_loop_cuda_graph_matches_stepwise(name):
         if graphs:
             assert agent.inner.graph is not None, getattr(agent.inner, "capture_error", "graph not captured")
             assert agent.inner.replays > 0
+            assert agent.match_graph.graph is not None, getattr(agent.match_graph, "capture_error", "not captured")
+            assert agent.match_graph.replays > 0
         else:
-            assert agent.inner.graph is None
+            assert agent.inner.graph is None and agent.match_graph.graph is None
         return [data.feat_syn.cpu().clone(), data.adj_syn.cpu().clone()] + [w.cpu().clone() for w in agent.inner.W]
 
     a, b, g = run(False), run(False), run(True)

@@ -17,6 +17,7 @@ class GCond(GCondBase):
     """
 
     x_variant = False
+    one_step = False      # DosCond / DosCondX: one matching step per outer step, no inner loop (doscond.py)
 
     def __init__(self, setting, data, args, **kwargs):
         super().__init__(setting, data, args, **kwargs)
@@ -75,7 +76,7 @@ class GCond(GCondBase):
         for ol in range(outer_loop):
             if not self.x_variant:
                 with K.timed("phase_pge_forward"):
-                    if self._pge_ready is None:
+                    if self.one_step or self._pge_ready is None:
                         adj_raw = pge.forward(self.feat_syn)
                         self.adj_syn, r_norm = K.dense_gcn_norm(adj_raw)
                     else:
@@ -97,11 +98,17 @@ class GCond(GCondBase):
             if self.trace:
                 self.trace("grads", step=(it, ol), loss=loss, feat_grad=feat_grad, pge_grads=pge_grads)
             with K.timed("phase_optimizer"):
-                if self._pge_turn(it, ol):
+                if self.one_step:                             # doscond.py:55-56: both, every outer step
+                    if pge_grads is not None:
+                        self.optimizer_pge.step(pge_grads)
+                    self.optimizer_feat.step([feat_grad])
+                elif self._pge_turn(it, ol):
                     if pge_grads is not None:
                         self.optimizer_pge.step(pge_grads)
                 else:
                     self.optimizer_feat.step([feat_grad])
+            if self.one_step:
+                continue                                      # the condense model is never trained (no inner loop)
             if self.x_variant:
                 adj_inner = self.adj_syn
             else:
@@ -116,6 +123,8 @@ class GCond(GCondBase):
 
     def publish(self, data):
         n = self.nnodes_syn
+        if self.one_step and not self.x_variant:
+            self.adj_syn_inner = self.pge.inference(self.feat_syn)        # doscond.py:61
         if self.x_variant or self.adj_syn_inner is None:
             adj = torch.eye(n)                                # gcondx.py:75-76
         else:

@@ -45,6 +45,24 @@ METHOD_CONFIGS = {
     },
 }
 
+# graphslim/configs/doscond/*.json and graphslim/configs/doscondx/*.json
+_DOS_SMALL = dict(lr_feat=0.01, lr_adj=0.01, dis_metric="mse", outer_loop=3, threshold=0.05, condense_model="GCN")
+_DOSX_SMALL = dict(lr_feat=0.01, lr_adj=0.01, dis_metric="mse", pre_norm=True, outer_loop=10, condense_model="GCN")
+METHOD_CONFIGS["doscond"] = {
+    "cora": _DOS_SMALL, "citeseer": dict(_DOS_SMALL, outer_loop=5), "pubmed": dict(_DOS_SMALL, outer_loop=5),
+    "flickr": dict(lr_feat=5e-3, lr_adj=5e-3, dis_metric="mse", outer_loop=10, threshold=0.01, condense_model="GCN"),
+    "ogbn-arxiv": dict(lr_feat=0.01, lr_adj=0.02, dis_metric="ours", outer_loop=5, threshold=0.01,
+                       condense_model="SGC", ntrans=1),
+    "reddit": dict(lr_feat=0.1, lr_adj=0.1, dis_metric="ours", outer_loop=10, threshold=0.01, condense_model="GCN",
+                   epochs=1000),
+}
+METHOD_CONFIGS["doscondx"] = {
+    "cora": _DOSX_SMALL, "citeseer": _DOSX_SMALL, "pubmed": _DOSX_SMALL,
+    "flickr": dict(lr_feat=0.01, lr_adj=0.01, dis_metric="mse", outer_loop=10, condense_model="GCN"),
+    "ogbn-arxiv": dict(lr_feat=0.1, lr_adj=0.1, dis_metric="mse", outer_loop=5, condense_model="SGC", ntrans=2),
+    "reddit": dict(lr_feat=0.1, lr_adj=0.1, dis_metric="mse", outer_loop=5, condense_model="GCN"),
+}
+
 # config.py:210-220 (the later 'pubmed' key wins)
 _REPRESENTATIVE_RATE = {"cora": 0.5, "citeseer": 0.5, "pubmed": 0.1, "flickr": 0.01, "reddit": 0.001,
                         "ogbn-arxiv": 0.01, "yelp": 0.001, "amazon": 0.002}

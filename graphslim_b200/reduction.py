@@ -1,4 +1,4 @@
-"""Method registry for the two reducers of this path (graphslim/reduction/registry.py:136-142).
+"""Method registry for the reducers of this path (GCond / GCondX and their one-step siblings DosCond / DosCondX) (graphslim/reduction/registry.py:136-142).
 
 ``create_reducer('gcond'|'gcondx', setting, data, args)`` returns the B200 implementation; every other name is
 forwarded to the reference registry when the reference package is importable, so this module can stand in for
@@ -9,6 +9,8 @@ from importlib import import_module
 _LOCAL = {
     "gcond": ("graphslim_b200.condensation.gcond", "GCond"),
     "gcondx": ("graphslim_b200.condensation.gcondx", "GCondX"),
+    "doscond": ("graphslim_b200.condensation.doscond", "DosCond"),
+    "doscondx": ("graphslim_b200.condensation.doscondx", "DosCondX"),
 }
 
 

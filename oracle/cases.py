@@ -52,6 +52,21 @@ CASES = {
         overrides=dict(outer_loop=6, inner_loop=2, hidden=32),
         keep_samples=1, keep_grads=2, grad_subsample=3,
     ),
+    # DosCond: one-step matching, PGE and features both stepped every outer step, no inner loop;
+    # cora JSON: GCN, 'mse'
+    "mini_doscond_gcn": dict(
+        dataset="cora", method="doscond", epochs=4,
+        graph=dict(n=600, und_edges=1500, d=96, c=5, split=(100, 100, 200), per_class_train=20, seed=3),
+        overrides=dict(outer_loop=3, hidden=32),
+        keep_samples=1, keep_grads=2, grad_subsample=3,
+    ),
+    # DosCondX: identity structure; ogbn-arxiv JSON: SGC ntrans=2, 'mse'
+    "mini_doscondx_sgc2": dict(
+        dataset="ogbn-arxiv", method="doscondx", epochs=3, reduction_rate=0.05,
+        graph=dict(n=1200, und_edges=6000, d=32, c=4, split=(600, 200, 400), seed=11),
+        overrides=dict(outer_loop=3, hidden=32),
+        keep_samples=1, keep_grads=2, grad_subsample=3,
+    ),
     # 'cos' metric on SGC ntrans=2
     "mini_sgc2_cos": dict(
         dataset="ogbn-arxiv", method="gcond", epochs=2, reduction_rate=0.05,

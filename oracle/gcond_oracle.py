@@ -20,7 +20,7 @@ Reference lines restated (all under /root/reference/graphslim):
   PGE .................... models/parametrized_adj.py:7-86
   matching loss .......... condensation/utils.py:12-106
   per-class matching ..... condensation/gcond_base.py:156-241
-  loops .................. condensation/gcond.py:17-81, condensation/gcondx.py:17-79
+  loops .................. condensation/gcond.py:17-81, condensation/gcondx.py:17-79, doscond.py:17-65, doscondx.py:19-63
 """
 import math
 from collections import Counter
@@ -325,7 +325,10 @@ class GCondOracle:
 
     def __init__(self, data, args, observer=None):
         self.data, self.args = data, args
-        self.x_variant = args.method == "gcondx"
+        self.x_variant = args.method in ("gcondx", "doscondx")
+        # DosCond / DosCondX (condensation/doscond.py:45-58, doscondx.py:44-53): one matching step per outer step,
+        # every optimiser steps every time, the condense model is never trained
+        self.one_step = args.method in ("doscond", "doscondx")
         self.obs = observer or (lambda *a: None)
         self.labels_syn_np, self.alloc = allocate_labels(data.labels_train, args.reduction_rate)
         self.n_syn = n = self.labels_syn_np.shape[0]
@@ -392,6 +395,16 @@ class GCondOracle:
                 loss.backward()
                 self.obs("grads", step, self.feat_syn.grad,
                          [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.pge.parameters()])
+                if self.one_step:
+                    if not self.x_variant:
+                        self.opt_pge.step()
+                    self.opt_feat.step()
+                    step += 1
+                    self.step_done_at.append(time.perf_counter())
+                    if max_outer_steps is not None and step >= max_outer_steps:
+                        self.losses = losses
+                        return losses
+                    continue
                 pge_turn = (ol % 5 < 1) if self.x_variant else (it % 50 < 10)
                 (self.opt_pge if pge_turn else self.opt_feat).step()
                 step += 1
@@ -414,5 +427,7 @@ class GCondOracle:
 
     def result(self):
         """What the reference writes to data.* at a checkpoint (gcond.py:76-78 / gcondx.py:74-76)."""
+        if self.one_step and not self.x_variant:
+            self.adj_inner_raw = self.pge.inference(self.feat_syn.detach())        # doscond.py:61
         adj = torch.eye(self.n_syn) if self.x_variant else self.adj_inner_raw.detach()
         return adj, self.feat_syn.detach(), torch.from_numpy(self.labels_syn_np).long()

@@ -108,7 +108,9 @@ def run_case(name):
             rec["adj_rowptr"], rec["adj_col"], rec["adj_val"] = rp.numpy().copy(), c.numpy().copy(), v.numpy().copy()
         return out
 
-    for m in (gmod, gxmod):
+    import graphslim.condensation.doscond as dmod
+    import graphslim.condensation.doscondx as dxmod
+    for m in (gmod, gxmod, dmod, dxmod):
         m.normalize_adj_tensor = norm_spy
 
     orig_sampler = data.retrieve_class_sampler
@@ -161,7 +163,8 @@ def run_case(name):
         return wrapped
 
     agent.optimizer_feat.step = grads_spy(agent.optimizer_feat.step)
-    agent.optimizer_pge.step = grads_spy(agent.optimizer_pge.step)
+    if args.method not in ("doscond", "doscondx"):      # DosCond steps both optimisers every outer step: count once
+        agent.optimizer_pge.step = grads_spy(agent.optimizer_pge.step)
 
     orig_init = BaseGNN.initialize
 

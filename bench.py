@@ -258,7 +258,7 @@ def run_ours(ns):
         seed_everything(args.seed)
         if world > 1:
             from graphslim_b200 import parallel
-            return parallel.ShardedGCond(args.setting, data, args)
+            return parallel.SHARDED[args.method](args.setting, data, args)
         return create_reducer(args.method, setting=args.setting, data=data, args=args)
 
     # ---- device-resident timing -----------------------------------------------------------------

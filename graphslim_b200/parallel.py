@@ -16,6 +16,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from .condensation.doscond import DosCond
+from .condensation.doscondx import DosCondX
 from .condensation.gcond import GCond
 from .condensation.gcondx import GCondX
 
@@ -91,6 +93,21 @@ class ShardedGCondX(_Sharded, GCondX):
     def __init__(self, setting, data, args, group=None, **kwargs):
         GCondX.__init__(self, setting, data, args, **kwargs)
         self._init_shard(data, group)
+
+
+class ShardedDosCond(_Sharded, DosCond):
+    def __init__(self, setting, data, args, group=None, **kwargs):
+        DosCond.__init__(self, setting, data, args, **kwargs)
+        self._init_shard(data, group)
+
+
+class ShardedDosCondX(_Sharded, DosCondX):
+    def __init__(self, setting, data, args, group=None, **kwargs):
+        DosCondX.__init__(self, setting, data, args, **kwargs)
+        self._init_shard(data, group)
+
+
+SHARDED = {"gcond": ShardedGCond, "gcondx": ShardedGCondX, "doscond": ShardedDosCond, "doscondx": ShardedDosCondX}
 
 
 # ============================================================================================================

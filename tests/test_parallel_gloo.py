@@ -28,8 +28,7 @@ def _worker(rank, world, port, name, out_dir):
     raw = helpers.case_graph(name)
     data = gdata.TransAndInd(raw, args.dataset, args.pre_norm)
     helpers.seed_everything(args.seed)
-    cls = parallel.ShardedGCondX if args.method == "gcondx" else parallel.ShardedGCond
-    agent = cls(args.setting, data, args)
+    agent = parallel.SHARDED[args.method](args.setting, data, args)
     losses = []
     agent.trace = lambda kind, **kw: losses.append(float(kw["loss"].item())) if kind == "grads" else None
     agent.reduce(data, verbose=False)
@@ -39,7 +38,8 @@ def _worker(rank, world, port, name, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world", [("mini_sgc2_arxiv", 2), ("mini_gcn_flickr", 2), ("mini_sgc2_arxiv", 3)])
+@pytest.mark.parametrize("name,world", [("mini_sgc2_arxiv", 2), ("mini_gcn_flickr", 2), ("mini_sgc2_arxiv", 3),
+                                        ("mini_doscond_gcn", 2)])
 def test_class_and_pge_sharding_matches_single_process(name, world, tmp_path):
     """Classes dealt to the ranks AND the PGE pair rows dealt to the ranks (uneven slices at world 3: N' = 40)."""
     port = 29500 + (os.getpid() % 2000)

@@ -68,6 +68,14 @@ SIGNATURES = {
     "gs_pge_bn1_bwd_pass_rows_f32": (c_int, [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                              c_i64, c_vp]),
     "gs_pge_bn1_bwd_final_f32": (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gs_pge_fused_workspace_bytes": (c_i64, [c_i32, c_int]),
+    "gs_pge_fused_l2_fwd_f32": (c_int, [c_i32, c_i32, c_i32, c_i32] + [c_vp] * 7 + [c_i64, c_vp, c_vp, c_int, c_vp, c_i64,
+                                                                               c_vp]),
+    "gs_pge_stats_finalize_f32": (c_int, [c_i32, c_vp, c_f64, c_f32, c_vp, c_vp, c_vp]),
+    "gs_pge_fused_l2_bwd_dx_f32": (c_int, [c_i32, c_i32, c_i32, c_i32] + [c_vp] * 7 + [c_i64] + [c_vp] * 9 +
+                                   [c_f64, c_vp, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
+    "gs_pge_fused_l2_bwd_dw_f32": (c_int, [c_i32, c_i32, c_i32, c_i32] + [c_vp] * 15 + [c_f64, c_vp, c_int, c_vp]),
+    "gs_pge_bn1_tsum_f64": (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gs_adam_step_f32": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_f64, c_f64, c_vp]),
     "gs_adam_table_f32": (c_int, [c_i32, c_f64, c_f64, c_f64, c_vp]),
     "gs_adam_step_table_f32": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64, c_f64, c_f64, c_vp]),

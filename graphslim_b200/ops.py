@@ -457,6 +457,84 @@ class CudaOps:
                    "gs_pge_bn1_bwd_final_f32")
         return dPa, dPb, dg, db
 
+    # ---- fused layer-2 pipeline (csrc/pge_fused.cu): H1 / dY2 / dH1 never reach HBM ---------------------------
+    def pge_fused_supported(self, h, nchunks):
+        """The fused tcgen05 pipeline covers the tensor-core precisions, unchunked BatchNorm and h in {128, 256}."""
+        return (self.precision in (1, 2) and int(h) in (128, 256) and int(nchunks) == 1
+                and getattr(self, "pge_fused", True))
+
+    def _pge_fused_ws(self, h):
+        nbytes = int(self.lib.gs_pge_fused_workspace_bytes(int(h), self.precision))
+        ws = getattr(self, "_pge_ws", None)
+        if ws is None or ws.numel() < nbytes:
+            ws = self._pge_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return ws
+
+    def pge_fused_l2_fwd(self, Pa, Pb, i_first, n_i, mean1, rstd1, gamma1, beta1, W2):
+        """Y2 rows (i, j), i in [i_first, i_first + n_i): relu(bn1(Pa[j] + Pb[i])) W2^T, and stats = [sum y | sum y^2]
+        (2h doubles) over those rows."""
+        n, h = Pa.shape
+        _mat(Pa, "Pa"), _mat(Pb, "Pb")
+        ldw = _mat(W2, "W2")
+        Y2 = self.empty(int(n_i) * n, h)
+        stats = torch.empty(2 * h, dtype=torch.float64, device=self.device)
+        ws = self._pge_fused_ws(h)
+        _lib.check(self.lib.gs_pge_fused_l2_fwd_f32(n, int(n_i), int(i_first), h, _ptr(Pa), _ptr(Pb), _ptr(mean1),
+                                                    _ptr(rstd1), _ptr(gamma1), _ptr(beta1), _ptr(W2), ldw, _ptr(Y2),
+                                                    _ptr(stats), self.precision, _ptr(ws), ws.numel(), self.stream),
+                   "gs_pge_fused_l2_fwd_f32")
+        return Y2, stats
+
+    def pge_stats_finalize(self, stats, count, eps=1e-5):
+        h = stats.numel() // 2
+        mean, rstd = self.empty(1, h), self.empty(1, h)
+        _lib.check(self.lib.gs_pge_stats_finalize_f32(h, _ptr(stats), float(count), eps, _ptr(mean), _ptr(rstd),
+                                                      self.stream), "gs_pge_stats_finalize_f32")
+        return mean, rstd
+
+    def pge_bn1_work(self, n, h):
+        """Zeroed [t1 | t2 (2h doubles) | Ga (n x h floats) | Gb (n x h floats)] buffer (float64 storage)."""
+        nbytes = int(self.lib.gs_pge_bn1_bwd_work_bytes(n, h))
+        return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
+
+    def pge_fused_l2_bwd_dx(self, Pa, Pb, i_first, n_i, bn1, W2, Y2, dE, bn2, w3, s1, s2, count, work=None,
+                            store=False):
+        """dH1 = dY2 W2 with dY2 computed on the fly from Y2 / dE.  store=True returns dH1 (n_i*n x h, unmasked);
+        otherwise the masked tile sums are accumulated into the Ga / Gb parts of `work` (pge_bn1_work)."""
+        n, h = Pa.shape
+        ldw = _mat(W2, "W2")
+        ws = self._pge_fused_ws(h)
+        dH1 = Ga = Gb = None
+        if store:
+            dH1 = self.empty(int(n_i) * n, h)
+        else:
+            base = work.data_ptr() + 16 * h
+            Ga, Gb = base, base + 4 * n * h
+        _lib.check(self.lib.gs_pge_fused_l2_bwd_dx_f32(n, int(n_i), int(i_first), h, _ptr(Pa), _ptr(Pb), _ptr(bn1[0]),
+                                                       _ptr(bn1[1]), _ptr(bn1[2]), _ptr(bn1[3]), _ptr(W2), ldw,
+                                                       _ptr(Y2), _ptr(dE), _ptr(bn2[0]), _ptr(bn2[1]), _ptr(bn2[2]),
+                                                       _ptr(bn2[3]), _ptr(w3), _ptr(s1), _ptr(s2), float(count),
+                                                       Ga or 0, Gb or 0, _ptr(dH1), self.precision, _ptr(ws),
+                                                       ws.numel(), self.stream), "gs_pge_fused_l2_bwd_dx_f32")
+        return dH1 if store else work
+
+    def pge_fused_l2_bwd_dw(self, Pa, Pb, i_first, n_i, bn1, Y2, dE, bn2, w3, s1, s2, count):
+        """dW2 (h x h) = dY2^T H1 over the slice's pair rows, both operands produced on chip."""
+        n, h = Pa.shape
+        dW2 = self.empty(h, h)
+        _lib.check(self.lib.gs_pge_fused_l2_bwd_dw_f32(n, int(n_i), int(i_first), h, _ptr(Pa), _ptr(Pb), _ptr(bn1[0]),
+                                                       _ptr(bn1[1]), _ptr(bn1[2]), _ptr(bn1[3]), _ptr(Y2), _ptr(dE),
+                                                       _ptr(bn2[0]), _ptr(bn2[1]), _ptr(bn2[2]), _ptr(bn2[3]),
+                                                       _ptr(w3), _ptr(s1), _ptr(s2), float(count), _ptr(dW2),
+                                                       self.precision, self.stream), "gs_pge_fused_l2_bwd_dw_f32")
+        return dW2
+
+    def pge_bn1_tsum(self, Pa, Pb, col_mean, rstd1, work):
+        n, h = Pa.shape
+        _lib.check(self.lib.gs_pge_bn1_tsum_f64(n, h, _ptr(Pa), _ptr(Pb), _ptr(col_mean), _ptr(rstd1), _ptr(work),
+                                                self.stream), "gs_pge_bn1_tsum_f64")
+        return work
+
     def pge_l1_expand(self, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
         n, h = Pa.shape
         H1 = self.empty(n * n, h)

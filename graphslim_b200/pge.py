@@ -135,6 +135,100 @@ class PGE:
         self._saved = None
         return grads, dX
 
+    # ---------------------------------------------------------------------------------- fused layer-2 pipeline
+    def _slice(self):
+        """(shard dict or None, first i, number of i) of this rank's pair rows."""
+        sh = getattr(self, "shard", None)
+        if sh is None:
+            return None, 0, self.n
+        return sh, sh["i0"], sh["i1"] - sh["i0"]
+
+    def _forward_fused(self, x, keep):
+        """csrc/pge_fused.cu: H1 is generated inside the layer-2 product's A-producer and the BatchNorm-2 column sums
+        come out of its epilogue, so one N'^2 x h array (Y2) is written and read once instead of 5 passes.  With row
+        sharding the same kernels run on the rank's slice of i; the column sums are all-reduced (2h doubles)."""
+        K, n, d, h = self.K, self.n, self.d, self.h
+        sh, i0, n_i = self._slice()
+        W1 = self.W[0]
+        Pa = K.gemm(x, W1[:, :d], tb=True)
+        Pb = K.gemm(x, W1[:, d:], tb=True)
+        mean1, rstd1, cm1 = K.pge_l1_stats_closed(Pa, Pb, self.eps)
+        with K.timed("pge_l2_fwd"):
+            Y2, stats = K.pge_fused_l2_fwd(Pa, Pb, i0, n_i, mean1, rstd1, self.gamma[0], self.beta[0], self.W[1])
+        if sh is not None:
+            import torch.distributed as dist
+            dist.all_reduce(stats, group=sh["group"])
+        mean2, rstd2 = K.pge_stats_finalize(stats, float(n) * float(n), self.eps)
+        off = self.chunk_off if sh is None else sh["off_rows"]
+        E = K.pge_l3(Y2, off, mean2, rstd2, self.gamma[1], self.beta[1], self.W[2].view(-1), self.b[2])
+        if sh is not None:
+            E = self._gather_rows(E, sh)
+        A = K.pge_symm_sigmoid(E, n)
+        if keep:
+            self._saved = (x, Pa, Pb, mean1, rstd1, cm1, None, Y2, mean2, rstd2, A)
+        return A
+
+    def _gather_rows(self, E_loc, sh):
+        """All-gather of the adjacency rows of every rank (slices may be uneven: padded to the largest)."""
+        import torch.distributed as dist
+        K = self.K
+        send = E_loc
+        if E_loc.numel() != sh["pad"]:
+            send = torch.zeros(sh["pad"], dtype=torch.float32, device=K.device)
+            send[:E_loc.numel()] = E_loc
+        full = torch.empty(sh["world"] * sh["pad"], dtype=torch.float32, device=K.device)
+        dist.all_gather_into_tensor(full, send, group=sh["group"])
+        if all(r == sh["pad"] for r in sh["rows"]):
+            return full
+        return torch.cat([full[r * sh["pad"]: r * sh["pad"] + sh["rows"][r]] for r in range(sh["world"])])
+
+    def _backward_fused(self, dA):
+        """Backward of `_forward_fused`: dY2 is recomputed from Y2 inside the producers of both layer-2 products, dH1 is
+        masked and reduced in the epilogue of the first, dW2 accumulates in TMEM in the second."""
+        K, n, d, h = self.K, self.n, self.d, self.h
+        sh, i0, n_i = self._slice()
+        x, Pa, Pb, mean1, rstd1, cm1, _, Y2, mean2, rstd2, A = self._saved
+        W1, W2, w3 = self.W[0], self.W[1], self.W[2].view(-1)
+        bn1 = (mean1, rstd1, self.gamma[0], self.beta[0])
+        bn2 = (mean2, rstd2, self.gamma[1], self.beta[1])
+        count = float(n) * float(n)
+        dE = K.pge_symm_sigmoid_bwd(dA, A)
+        off = self.chunk_off
+        if sh is not None:
+            dE = dE[i0 * n: (i0 + n_i) * n]
+            off = sh["off_rows"]
+        s1, s2, dw3, db3 = K.pge_l3_bwd_stats(Y2, dE, off, mean2, rstd2, self.gamma[1], self.beta[1], w3)
+        if sh is not None:
+            import torch.distributed as dist
+            flat = torch.cat([s1.view(-1), s2.view(-1), dw3.view(-1), db3.view(-1)])
+            dist.all_reduce(flat, group=sh["group"])                          # BN2 backward sums + layer-3 grads
+            s1, s2, dw3, db3 = flat[:h].view(1, h), flat[h:2 * h].view(1, h), flat[2 * h:3 * h], flat[3 * h:3 * h + 1]
+        dgamma2, dbeta2 = s2.sum(0), s1.sum(0)
+        work = K.pge_bn1_work(n, h)
+        with K.timed("pge_l2_bwd_dx"):
+            K.pge_fused_l2_bwd_dx(Pa, Pb, i0, n_i, bn1, W2, Y2, dE, bn2, w3, s1, s2, count, work=work)
+        with K.timed("pge_l2_bwd_dw"):
+            dW2 = K.pge_fused_l2_bwd_dw(Pa, Pb, i0, n_i, bn1, Y2, dE, bn2, w3, s1, s2, count)
+        K.pge_bn1_tsum(Pa, Pb, cm1, rstd1, work)
+        if sh is not None:
+            dist.all_reduce(work[:2 * h], group=sh["group"])                  # t1, t2 (float64)
+            red = torch.cat([work[2 * h:].view(torch.float32), dW2.view(-1)])
+            dist.all_reduce(red, group=sh["group"])                           # Ga, Gb and dW2 (float32)
+            nfl = 2 * n * h
+            work[2 * h:].view(torch.float32).copy_(red[:nfl])
+            dW2 = red[nfl:].view(h, h)
+        dPa, dPb, dgamma1, dbeta1 = K.pge_bn1_bwd_final(Pa, Pb, rstd1, self.gamma[0], cm1, work)
+        dW1 = K.empty(h, 2 * d)
+        K.gemm(dPa, x, ta=True, out=dW1[:, :d])
+        K.gemm(dPb, x, ta=True, out=dW1[:, d:])
+        dX = K.gemm(dPa, W1[:, :d])
+        K.gemm(dPb, W1[:, d:], out=dX, beta=1.0)
+        zeros_h = K.zeros(h)
+        grads = [dW1, zeros_h, dW2, zeros_h.clone(), dw3.reshape(1, h), db3.reshape(1), dgamma1, dbeta1, dgamma2,
+                 dbeta2]
+        self._saved = None
+        return grads, dX
+
     def parameters(self):
         return [self.W[0], self.b[0], self.W[1], self.b[1], self.W[2], self.b[2],
                 self.gamma[0], self.beta[0], self.gamma[1], self.beta[1]]
@@ -142,6 +236,8 @@ class PGE:
     # ---------------------------------------------------------------------------------- forward
     def forward(self, x, keep=True):
         """adj (n,n) = zero-diag(sigmoid((E+E^T)/2)),  E[i,j] = MLP([x_j, x_i]).  BN always uses batch stats."""
+        if self.K.pge_fused_supported(self.h, self.nchunks):
+            return self._forward_fused(x, keep)
         if getattr(self, "shard", None) is not None:
             return self._forward_sharded(x, keep)
         K, n, d, h = self.K, self.n, self.d, self.h
@@ -173,6 +269,8 @@ class PGE:
     # ---------------------------------------------------------------------------------- backward
     def backward(self, dA):
         """Returns (grads in parameters() order, dX)."""
+        if self._saved[6] is None:                               # saved by the fused forward: H1 was never materialised
+            return self._backward_fused(dA)
         if getattr(self, "shard", None) is not None:
             return self._backward_sharded(dA)
         K, n, d, h = self.K, self.n, self.d, self.h

@@ -241,6 +241,41 @@ int gs_pge_bn1_bwd_final_f32(int32_t n, int32_t h, const float* Pa, const float*
                              const float* gamma, const float* col_mean, const void* work, float* dPa, float* dPb,
                              float* dgamma, float* dbeta, void* stream);
 
+/* ---- fused PGE layer-2 pipeline (csrc/pge_fused.cu): tcgen05 + TMEM products whose N'^2 x h operands are produced on
+ * chip, replacing gs_pge_l1_expand + gs_gemm + gs_col_stats (forward) and gs_pge_bn2_bwd_apply + two gs_gemm +
+ * gs_pge_bn1_bwd_pass (backward) of models/parametrized_adj.py:57-71 and its autograd.  Unchunked BatchNorm, h = 128 or
+ * 256, precision 1 (3xBF16) or 2 (BF16); pair rows (i, j) with i in [i_first, i_first + n_i) (a rank's slice), all j.
+ *   gs_pge_fused_l2_fwd_f32     Y2 (n_i*n x h) = relu(bn1(Pa[j] + Pb[i])) W2^T, H1 generated in the A-producer;
+ *                               stats = [sum y | sum y^2] (2h doubles, overwritten) from the epilogue
+ *   gs_pge_stats_finalize_f32   mean / rstd of BatchNorm 2 from the (all-reduced) sums and the global row count
+ *   gs_pge_fused_l2_bwd_dx_f32  dH1 = dY2 W2 with dY2 = bn2'(relu'(bn2(Y2)) dE w3) computed from the TMA-loaded raw Y2
+ *                               tile; dH1 != NULL stores it, else it is masked by H1 > 0 and reduced into Ga[j] = sum_i,
+ *                               Gb[i] = sum_j (n x h each, accumulated into: the caller zeroes them)
+ *   gs_pge_fused_l2_bwd_dw_f32  dW2 (h x h, overwritten) = dY2^T H1, both operands produced on chip (MN-major UMMA)
+ *   gs_pge_bn1_tsum_f64         adds t1 = sum g, t2 = sum g*xhat implied by Ga / Gb into work = [t1 | t2 | Ga | Gb]
+ *                               (layout of gs_pge_bn1_bwd_pass_rows_f32), ready for gs_pge_bn1_bwd_final_f32
+ * workspace: gs_pge_fused_workspace_bytes(h, precision) bytes (BF16 tile image of W2), 16-byte aligned. */
+int64_t gs_pge_fused_workspace_bytes(int32_t h, int precision);
+int gs_pge_fused_l2_fwd_f32(int32_t n, int32_t n_i, int32_t i_first, int32_t h, const float* Pa, const float* Pb,
+                            const float* mean1, const float* rstd1, const float* gamma1, const float* beta1,
+                            const float* W2, int64_t ldw, float* Y2, double* stats, int precision, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+int gs_pge_stats_finalize_f32(int32_t h, const double* stats, double count, float eps, float* mean, float* rstd,
+                              void* stream);
+int gs_pge_fused_l2_bwd_dx_f32(int32_t n, int32_t n_i, int32_t i_first, int32_t h, const float* Pa, const float* Pb,
+                               const float* mean1, const float* rstd1, const float* gamma1, const float* beta1,
+                               const float* W2, int64_t ldw, const float* Y2, const float* dE, const float* mean2,
+                               const float* rstd2, const float* gamma2, const float* beta2, const float* w3,
+                               const float* s1, const float* s2, double count, float* Ga, float* Gb, float* dH1,
+                               int precision, void* workspace, int64_t workspace_bytes, void* stream);
+int gs_pge_fused_l2_bwd_dw_f32(int32_t n, int32_t n_i, int32_t i_first, int32_t h, const float* Pa, const float* Pb,
+                               const float* mean1, const float* rstd1, const float* gamma1, const float* beta1,
+                               const float* Y2, const float* dE, const float* mean2, const float* rstd2,
+                               const float* gamma2, const float* beta2, const float* w3, const float* s1,
+                               const float* s2, double count, float* dW2, int precision, void* stream);
+int gs_pge_bn1_tsum_f64(int32_t n, int32_t h, const float* Pa, const float* Pb, const float* col_mean,
+                        const float* rstd1, void* work, void* stream);
+
 /* ---- optimiser (torch.optim.Adam defaults; condensation/gcond_base.py:68-69, gcond.py:44) ---- */
 int gs_adam_step_f32(int64_t n, float* p, const float* g, float* m, float* v, int32_t step, double lr, double beta1,
                      double beta2, double eps, void* stream);

@@ -13,10 +13,11 @@ from graphslim_b200.ops import Csr
 
 
 class EmuOps:
-    def __init__(self, device="cpu", precision=0):
+    def __init__(self, device="cpu", precision=0, fused=True):
         self.device = torch.device(device)
         self.precision = precision
         self._launches = 0
+        self.pge_fused = bool(fused)       # True: the algebra of the fused layer-2 pipeline (the product's default path)
 
     def empty(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype, device=self.device)
@@ -291,6 +292,59 @@ class EmuOps:
         dPa = gamma * rs * (Ga - a1n - rs * n * (Pa - col_mean[0]) * a2)
         dPb = gamma * rs * (Gb - a1n - rs * n * (Pb - col_mean[1]) * a2)
         return dPa, dPb, tsum[h:].float(), tsum[:h].float()
+
+    # ---- fused layer-2 pipeline (same contracts as CudaOps; plain fp32 algebra)
+    def pge_fused_supported(self, h, nchunks):
+        return bool(self.pge_fused) and int(nchunks) == 1 and int(h) in (128, 256)
+
+    def _h1_rows(self, Pa, Pb, i_first, n_i, bn1):
+        mean, rstd, gamma, beta = bn1
+        return self.pge_l1_expand_rows(Pa, Pb[i_first:i_first + n_i], None, mean, rstd, gamma, beta)
+
+    def _dy2_rows(self, Y2, dE, bn2, w3, s1, s2, count):
+        mean, rstd, gamma, beta = bn2
+        xh = (Y2 - mean) * rstd
+        d = dE[:, None] * w3[None, :] * ((gamma * xh + beta) > 0)
+        return gamma * rstd * (d - s1.view(1, -1) / count - xh * s2.view(1, -1) / count)
+
+    def pge_fused_l2_fwd(self, Pa, Pb, i_first, n_i, mean1, rstd1, gamma1, beta1, W2):
+        H1 = self._h1_rows(Pa, Pb, i_first, n_i, (mean1, rstd1, gamma1, beta1))
+        Y2 = H1 @ W2.T
+        y = Y2.double()
+        return Y2, torch.cat([y.sum(0), (y * y).sum(0)])
+
+    def pge_stats_finalize(self, stats, count, eps=1e-5):
+        h = stats.numel() // 2
+        m = stats[:h] / count
+        var = (stats[h:] / count - m * m).clamp_(min=0)
+        return m.float().view(1, h), (1.0 / torch.sqrt(var + eps)).float().view(1, h)
+
+    def pge_bn1_work(self, n, h):
+        return torch.zeros(2 * h + n * h, dtype=torch.float64)
+
+    def pge_fused_l2_bwd_dx(self, Pa, Pb, i_first, n_i, bn1, W2, Y2, dE, bn2, w3, s1, s2, count, work=None,
+                            store=False):
+        n, h = Pa.shape
+        dH1 = self._dy2_rows(Y2, dE, bn2, w3, s1, s2, count) @ W2
+        if store:
+            return dH1
+        g = (dH1 * (self._h1_rows(Pa, Pb, i_first, n_i, bn1) > 0)).view(n_i, n, h)
+        fl = work[2 * h:].view(torch.float32)
+        fl[:n * h] += g.sum(0).reshape(-1)
+        fl[n * h:].view(n, h)[i_first:i_first + n_i] += g.sum(1)
+        return work
+
+    def pge_fused_l2_bwd_dw(self, Pa, Pb, i_first, n_i, bn1, Y2, dE, bn2, w3, s1, s2, count):
+        return self._dy2_rows(Y2, dE, bn2, w3, s1, s2, count).T @ self._h1_rows(Pa, Pb, i_first, n_i, bn1)
+
+    def pge_bn1_tsum(self, Pa, Pb, col_mean, rstd1, work):
+        n, h = Pa.shape
+        fl = work[2 * h:].view(torch.float32)
+        Ga, Gb = fl[:n * h].view(n, h).double(), fl[n * h:].view(n, h).double()
+        work[:h] += Ga.sum(0)
+        work[h:2 * h] += rstd1.view(-1).double() * ((Ga * (Pa.double() - col_mean[0].double())).sum(0)
+                                                    + (Gb * (Pb.double() - col_mean[1].double())).sum(0))
+        return work
 
     def pge_l1_expand(self, Pa, Pb, chunk_off, mean, rstd, gamma, beta):
         y = self._y1(Pa, Pb)

@@ -45,7 +45,7 @@ constexpr int kThreads = 14 * 32;
 constexpr uint32_t kPlaneA = BM * BK * 2;          // 16 KB: one bf16 plane of the A stage == one raw 32-column box
 constexpr uint32_t kStageA = 2 * kPlaneA;          // hi | lo  ==  raw cols 0-31 | raw cols 32-63 (in-place conversion)
 constexpr uint32_t kStagingBytes = 4 * 32 * 36 * 4;   // epilogue transposition tiles, one per warp
-constexpr uint32_t kGaBytes = 2 * 4 * BJ * 32 * 4;    // cross-warp exchange of the Ga partials (double buffered)
+constexpr uint32_t kGaBytes = BJ * 256 * 4;           // the tile's Ga block (BJ x H floats), shared by the epilogue warps
 constexpr int DW_BI = 4;                             // dW kernel: a k-stage is DW_BI x BJ = 32 pair rows
 constexpr int DW_ROWS = DW_BI * BJ;
 constexpr int kDwStages = 3;
@@ -515,10 +515,12 @@ pge_l2_bwd_dx_kernel(const __grid_constant__ CUtensorMap map_y2, BwdParams p) {
         mbar_arrive(smem_u32(&bars.tempty[acc]));
       }
     } else {
-      // thread = tile row u = 32 q + lane: il = 4 q + lane / 8, jl = lane % 8.  g = dH1 * [H1 > 0] is staged, then lane c
-      // sums column c: over the 8 jl of each of the warp's 4 il (-> Gb, kept in registers while the i-block lasts) and
-      // over the warp's 4 il for each jl (-> Ga, combined across the 4 warps through shared memory, then one atomic
-      // per (j, column) and tile).
+      // The raw 32 x 32 accumulator block is staged (thread = tile row u = 32 q + lane, il = 4 q + u / 8, jl = u % 8);
+      // then LANE c OWNS COLUMN c: it regenerates the ReLU mask of its column for the warp's 32 rows from 8 Pa values,
+      // 4 Pb values and the column's BatchNorm constants (coalesced scalar loads), and sums the masked entries over
+      // the 8 jl of each il (-> Gb, kept in registers while the i-block lasts) and over the warp's 4 il for each jl
+      // (-> Ga: shared-memory atomics into an 8 x H tile shared by the four warps, flushed once per tile with float4
+      // global atomics).  Rows outside the slice carry dY2 = 0, hence exact zeros here.
       float gb_acc[C::NB][4];
 #pragma unroll
       for (int b = 0; b < C::NB; ++b)
@@ -536,37 +538,34 @@ pge_l2_bwd_dx_kernel(const __grid_constant__ CUtensorMap map_y2, BwdParams p) {
           }
       };
       const int et = q * 32 + lane;           // epilogue thread id 0..127
-      int buf = 0;
+      for (int idx = et; idx < BJ * H; idx += kEpiThreads) ga_sm[idx] = 0.f;
+      named_bar_sync(1, kEpiThreads);
       for (int t = t0; t < t1; ++t, ++tcount) {
         const int ib = t / p.g.tiles_j, jb = t - ib * p.g.tiles_j;
         if (ib != cur_ib) {
           if (cur_ib >= 0) flush_gb(cur_ib);
           cur_ib = ib;
         }
-        const int li = ib * BI + 4 * q + (lane >> 3), j = jb * BJ + (lane & 7);
-        const bool valid = li < p.g.n_i && j < p.g.n;
-        const float* pa_row = p.Pa + (int64_t)(valid ? j : 0) * H;
-        const float* pb_row = p.Pb + (int64_t)(p.g.i_first + (valid ? li : 0)) * H;
+        const float* pa_base = p.Pa + (int64_t)(jb * BJ) * H + lane;
+        const float* pb_base = p.Pb + (int64_t)(p.g.i_first + ib * BI + 4 * q) * H + lane;
+        const int nj = min(BJ, p.g.n - jb * BJ), ni = min(4, p.g.n_i - (ib * BI + 4 * q));   // valid rows (ni may be <= 0)
         const int acc = tcount & 1;
         mbar_wait(smem_u32(&bars.tfull[acc]), (tcount >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int b = 0; b < C::NB; ++b) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + b * 32), r);
-          tmem_ld_wait();
+          const int c = b * 32;
+          float pa[BJ], pb[4];
 #pragma unroll
-          for (int k4 = 0; k4 < 8; ++k4) {
-            const int c = b * 32 + k4 * 4;
-            const float4 h1 = h1_value4(ld4(pa_row + c), ld4(pb_row + c), ld4(p.bn1.mean + c), ld4(p.bn1.rstd + c),
-                                        ld4(p.bn1.gamma + c), ld4(p.bn1.beta + c));
-            float4 v;
-            v.x = (valid && h1.x > 0.f) ? __uint_as_float(r[k4 * 4 + 0]) : 0.f;
-            v.y = (valid && h1.y > 0.f) ? __uint_as_float(r[k4 * 4 + 1]) : 0.f;
-            v.z = (valid && h1.z > 0.f) ? __uint_as_float(r[k4 * 4 + 2]) : 0.f;
-            v.w = (valid && h1.w > 0.f) ? __uint_as_float(r[k4 * 4 + 3]) : 0.f;
-            *reinterpret_cast<float4*>(st + lane * 36 + k4 * 4) = v;
-          }
+          for (int jj = 0; jj < BJ; ++jj) pa[jj] = __ldg(pa_base + (int64_t)(jj < nj ? jj : 0) * H + c);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pb[k] = (ni > 0) ? __ldg(pb_base + (int64_t)(k < ni ? k : 0) * H + c) : 0.f;
+          const float mu = __ldg(p.bn1.mean + c + lane), rs = __ldg(p.bn1.rstd + c + lane),
+                      g = __ldg(p.bn1.gamma + c + lane), bt = __ldg(p.bn1.beta + c + lane);
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + c), r);
+          tmem_ld_wait();
+          stage_block(st, lane, r);
           __syncwarp();
           float ga[BJ];
 #pragma unroll
@@ -576,29 +575,28 @@ pge_l2_bwd_dx_kernel(const __grid_constant__ CUtensorMap map_y2, BwdParams p) {
             float gsum = 0.f;
 #pragma unroll
             for (int jj = 0; jj < BJ; ++jj) {
-              const float x = st[(k * 8 + jj) * 36 + lane];
+              float x = st[(k * 8 + jj) * 36 + lane];
+              x = (fmaf(g, (pa[jj] + pb[k] - mu) * rs, bt) > 0.f) ? x : 0.f;
               gsum += x;
               ga[jj] += x;
             }
             gb_acc[b][k] += gsum;
           }
-          float* gbuf = ga_sm + buf * (4 * BJ * 32);
 #pragma unroll
-          for (int jj = 0; jj < BJ; ++jj) gbuf[(q * BJ + jj) * 32 + lane] = ga[jj];
-          named_bar_sync(1, kEpiThreads);       // also orders this block's staging reads before the next block's writes
-#pragma unroll
-          for (int rep = 0; rep < 2; ++rep) {
-            const int idx = et + rep * kEpiThreads;      // (jl2, c2) of the 8 x 32 block
-            const int jl2 = idx >> 5, c2 = idx & 31;
-            const float v = gbuf[(0 * BJ + jl2) * 32 + c2] + gbuf[(1 * BJ + jl2) * 32 + c2] +
-                            gbuf[(2 * BJ + jl2) * 32 + c2] + gbuf[(3 * BJ + jl2) * 32 + c2];
-            const int j2 = jb * BJ + jl2;
-            if (j2 < p.g.n) atomicAdd(p.Ga + (int64_t)j2 * H + b * 32 + c2, v);
-          }
-          buf ^= 1;
+          for (int jj = 0; jj < BJ; ++jj) atomicAdd(ga_sm + jj * H + c + lane, ga[jj]);
+          __syncwarp();                         // the staging tile is rewritten by the next block
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&bars.tempty[acc]));
+        named_bar_sync(1, kEpiThreads);         // all four warps have added their share of this tile's Ga block
+        for (int idx = et; idx < BJ * H / 4; idx += kEpiThreads) {
+          const float4 v = reinterpret_cast<float4*>(ga_sm)[idx];
+          reinterpret_cast<float4*>(ga_sm)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int jj = idx / (H / 4);
+          if (jb * BJ + jj < p.g.n)
+            atomicAdd(reinterpret_cast<float4*>(p.Ga + (int64_t)(jb * BJ + jj) * H) + (idx % (H / 4)), v);
+        }
+        named_bar_sync(1, kEpiThreads);         // zeroed before the next tile's adds
       }
       if (cur_ib >= 0) flush_gb(cur_ib);
     }

@@ -68,44 +68,56 @@ struct Bn {              // BatchNorm affine pieces of one layer (h values each)
   const float *mean, *rstd, *gamma, *beta;
 };
 
-// relu(gamma * ((a + p - mean) * rstd) + beta): the formula of pge_l1_expand_kernel (pge.cu), so the regenerated
-// ReLU masks agree with it bit for bit
-__device__ __forceinline__ float h1_value(float a, float p, float mu, float rs, float g, float b) {
-  return fmaxf(fmaf(g, (a + p - mu) * rs, b), 0.f);
+// BatchNorm-1 + ReLU of a generated layer-1 pre-activation with the affine pieces folded per column:
+//   relu(gamma * ((a + p - mean) * rstd) + beta) = relu((a + p) * grs + off),  grs = gamma * rstd, off = beta - mean * grs.
+// Every generator of H1 (forward producer, dW producer, the mask of the dX epilogue) uses this one form.
+struct H1Consts {
+  float4 grs, off;
+};
+__device__ __forceinline__ H1Consts load_h1_consts(const Bn& bn1, int c) {
+  const float4 mu = ld4(bn1.mean + c), rs = ld4(bn1.rstd + c), g = ld4(bn1.gamma + c), b = ld4(bn1.beta + c);
+  H1Consts k;
+  k.grs = make_float4(g.x * rs.x, g.y * rs.y, g.z * rs.z, g.w * rs.w);
+  k.off = make_float4(fmaf(-mu.x, k.grs.x, b.x), fmaf(-mu.y, k.grs.y, b.y), fmaf(-mu.z, k.grs.z, b.z),
+                      fmaf(-mu.w, k.grs.w, b.w));
+  return k;
 }
-__device__ __forceinline__ float4 h1_value4(const float4& a, const float4& p, const float4& mu, const float4& rs,
-                                            const float4& g, const float4& b) {
-  return make_float4(h1_value(a.x, p.x, mu.x, rs.x, g.x, b.x), h1_value(a.y, p.y, mu.y, rs.y, g.y, b.y),
-                     h1_value(a.z, p.z, mu.z, rs.z, g.z, b.z), h1_value(a.w, p.w, mu.w, rs.w, g.w, b.w));
+__device__ __forceinline__ float h1_pre(float a, float p, float grs, float off) { return fmaf(a + p, grs, off); }
+__device__ __forceinline__ float4 h1_value4(const float4& a, const float4& p, const H1Consts& k) {
+  return make_float4(fmaxf(h1_pre(a.x, p.x, k.grs.x, k.off.x), 0.f), fmaxf(h1_pre(a.y, p.y, k.grs.y, k.off.y), 0.f),
+                     fmaxf(h1_pre(a.z, p.z, k.grs.z, k.off.z), 0.f), fmaxf(h1_pre(a.w, p.w, k.grs.w, k.off.w), 0.f));
 }
 
-// constants of the dY2 producer for four columns
+// d loss / d Y2 of one element = BatchNorm-2 backward of (relu'(bn2(y)) dE w3)   (pge_bn2_bwd_apply_kernel), folded:
+//   xh = y * rs + nm (nm = -mean * rs);  on = gamma * xh + beta > 0;
+//   dy2 = c0 * (on * dE * w3 - s1/M - xh * s2/M) = fma(xh, na2, on ? fma(dE, wc, na1) : na1)
+// with c0 = gamma * rs, wc = w3 * c0, na1 = -(s1/M) c0, na2 = -(s2/M) c0.
 struct Dy2Consts {
-  float4 mu, rs, g, b, w, a1, a2, c0;
+  float4 rs, nm, g, b, wc, na1, na2;
 };
 __device__ __forceinline__ Dy2Consts load_dy2_consts(const Bn& bn2, const float* w3, const float* s1, const float* s2,
                                                      float inv_count, int c) {
+  const float4 mu = ld4(bn2.mean + c), w = ld4(w3 + c), a1 = ld4(s1 + c), a2 = ld4(s2 + c);
   Dy2Consts k;
-  k.mu = ld4(bn2.mean + c); k.rs = ld4(bn2.rstd + c); k.g = ld4(bn2.gamma + c); k.b = ld4(bn2.beta + c);
-  k.w = ld4(w3 + c); k.a1 = ld4(s1 + c); k.a2 = ld4(s2 + c);
-  k.a1.x *= inv_count; k.a1.y *= inv_count; k.a1.z *= inv_count; k.a1.w *= inv_count;
-  k.a2.x *= inv_count; k.a2.y *= inv_count; k.a2.z *= inv_count; k.a2.w *= inv_count;
-  k.c0 = make_float4(k.g.x * k.rs.x, k.g.y * k.rs.y, k.g.z * k.rs.z, k.g.w * k.rs.w);
+  k.rs = ld4(bn2.rstd + c); k.g = ld4(bn2.gamma + c); k.b = ld4(bn2.beta + c);
+  k.nm = make_float4(-mu.x * k.rs.x, -mu.y * k.rs.y, -mu.z * k.rs.z, -mu.w * k.rs.w);
+  const float4 c0 = make_float4(k.g.x * k.rs.x, k.g.y * k.rs.y, k.g.z * k.rs.z, k.g.w * k.rs.w);
+  k.wc = make_float4(w.x * c0.x, w.y * c0.y, w.z * c0.z, w.w * c0.w);
+  k.na1 = make_float4(-a1.x * inv_count * c0.x, -a1.y * inv_count * c0.y, -a1.z * inv_count * c0.z, -a1.w * inv_count * c0.w);
+  k.na2 = make_float4(-a2.x * inv_count * c0.x, -a2.y * inv_count * c0.y, -a2.z * inv_count * c0.z, -a2.w * inv_count * c0.w);
   return k;
 }
-// d loss / d Y2 of one element: BatchNorm-2 backward of (relu'(bn2(y)) * dE * w3)   (pge_bn2_bwd_apply_kernel)
-__device__ __forceinline__ float dy2_value(float y, float de, float mu, float rs, float g, float b, float w, float a1,
-                                           float a2, float c0) {
-  const float xh = (y - mu) * rs;
-  const float yh = fmaf(g, xh, b);
-  const float d = (yh > 0.f) ? de * w : 0.f;
-  return c0 * (d - a1 - xh * a2);
+__device__ __forceinline__ float dy2_value(float y, float de, float rs, float nm, float g, float b, float wc, float na1,
+                                           float na2) {
+  const float xh = fmaf(y, rs, nm);
+  const float sel = (fmaf(g, xh, b) > 0.f) ? fmaf(de, wc, na1) : na1;
+  return fmaf(xh, na2, sel);
 }
 __device__ __forceinline__ float4 dy2_value4(const float4& y, float de, const Dy2Consts& k) {
-  return make_float4(dy2_value(y.x, de, k.mu.x, k.rs.x, k.g.x, k.b.x, k.w.x, k.a1.x, k.a2.x, k.c0.x),
-                     dy2_value(y.y, de, k.mu.y, k.rs.y, k.g.y, k.b.y, k.w.y, k.a1.y, k.a2.y, k.c0.y),
-                     dy2_value(y.z, de, k.mu.z, k.rs.z, k.g.z, k.b.z, k.w.z, k.a1.z, k.a2.z, k.c0.z),
-                     dy2_value(y.w, de, k.mu.w, k.rs.w, k.g.w, k.b.w, k.w.w, k.a1.w, k.a2.w, k.c0.w));
+  return make_float4(dy2_value(y.x, de, k.rs.x, k.nm.x, k.g.x, k.b.x, k.wc.x, k.na1.x, k.na2.x),
+                     dy2_value(y.y, de, k.rs.y, k.nm.y, k.g.y, k.b.y, k.wc.y, k.na1.y, k.na2.y),
+                     dy2_value(y.z, de, k.rs.z, k.nm.z, k.g.z, k.b.z, k.wc.z, k.na1.z, k.na2.z),
+                     dy2_value(y.w, de, k.rs.w, k.nm.w, k.g.w, k.b.w, k.wc.w, k.na1.w, k.na2.w));
 }
 
 // four fp32 values -> 8 bytes of the hi plane (+ 8 bytes of the lo plane) at a swizzled operand offset
@@ -232,6 +244,13 @@ struct FwdParams {
   double* stats;             // [sum y (H) | sum y^2 (H)], accumulated with atomics
 };
 
+// Warp roles of the forward: 4 producer warps (generating H1 is light), 8 epilogue warps (two per TMEM lane quarter,
+// alternating 32-column blocks: the epilogue -- TMEM read, transposition, Y2 store, column sums -- is what bounds this
+// kernel), the MMA issuer and the TMA issuer.
+constexpr int kFwdProducerWarps = 4;
+constexpr int kFwdEpiWarps = 8;
+constexpr uint32_t kFwdStagingBytes = kFwdEpiWarps * 32 * 32 * 4;     // dense swizzled 32 x 32 tiles, one per warp
+
 template <int H, int NPASS>
 __global__ void __launch_bounds__(kThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
   using C = Cfg<H, NPASS>;
@@ -244,47 +263,52 @@ __global__ void __launch_bounds__(kThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
   int t0, t1;
   cta_range(p.g.num_tiles, t0, t1);
 
-  if (threadIdx.x == 0) init_bars<C::kStages>(bars, kProducerWarps + 1, kEpiThreads);
+  if (threadIdx.x == 0) init_bars<C::kStages>(bars, kFwdProducerWarps + 1, kFwdEpiWarps * 32);
   if (warp == kMmaWarp) tmem_alloc(smem_u32(&bars.tmem_holder), C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_holder;
 
-  if (warp < kProducerWarps) {
+  if (warp < kFwdProducerWarps) {
     // ============================== producers: generate the H1 tile ==============================
+    // thread = (c4, jl): tile rows u = jl + 8 il for all 16 il; one Pa vector, 16 Pb vectors per k-block
     const int tid = threadIdx.x;
-    const int c4 = tid & 15, jl = (tid >> 4) & 7, ilb = tid >> 7;     // rows u = (tid >> 4) + 16 i: il = ilb + 2 i
+    const int c4 = tid & 15, jl = tid >> 4;
     uint32_t it = 0;
     for (int t = t0; t < t1; ++t) {
       const int ib = t / p.g.tiles_j, jb = t - ib * p.g.tiles_j;
       const int j = jb * BJ + jl;
       const bool jv = j < p.g.n;
       const float* pa_row = p.Pa + (int64_t)(jv ? j : 0) * H;
+      const float* pb_rows = p.Pb + (int64_t)(p.g.i_first + ib * BI) * H;
+      const int ni = min(BI, p.g.n_i - ib * BI);                 // valid il of this tile (>= 1)
 #pragma unroll 1
       for (int kb = 0; kb < C::KB; ++kb, ++it) {
         const int c = kb * BK + c4 * 4;
+        const H1Consts k1 = load_h1_consts(p.bn1, c);
         const float4 pa = ld4(pa_row + c);
         float4 pb[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int li = ib * BI + ilb + 2 * i;
-          pb[i] = ld4(p.Pb + (int64_t)(p.g.i_first + (li < p.g.n_i ? li : 0)) * H + c);
-        }
-        const float4 mu = ld4(p.bn1.mean + c), rs = ld4(p.bn1.rstd + c), g = ld4(p.bn1.gamma + c),
-                     b = ld4(p.bn1.beta + c);
+        for (int i = 0; i < 8; ++i) pb[i] = ld4(pb_rows + (int64_t)(i < ni ? i : 0) * H + c);
         const int s = it % C::kStages;
         const uint32_t ph = (it / C::kStages) & 1;
         mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1);
         uint8_t* sa_hi = smem + s * C::kStageBytes;
         uint8_t* sa_lo = sa_hi + kPlaneA;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int u = (tid >> 4) + 16 * i;
-          const bool valid = jv && (ib * BI + ilb + 2 * i < p.g.n_i);
-          float4 o = h1_value4(pa, pb[i], mu, rs, g, b);
-          if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
-          store_split4<C::kWithLo>(sa_hi, sa_lo, sw128_offset(u, c4 * 4), o);
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pb[i] = ld4(pb_rows + (int64_t)(8 + i < ni ? 8 + i : 0) * H + c);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int il = half * 8 + i;
+            float4 o = h1_value4(pa, pb[i], k1);
+            if (!(jv && il < ni)) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            store_split4<C::kWithLo>(sa_hi, sa_lo, sw128_offset(il * BJ + jl, c4 * 4), o);
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -311,13 +335,20 @@ __global__ void __launch_bounds__(kThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
     mma_role_rowtiles<H, NPASS>(smem, bars, tmem_base, t0, t1, lane);
   } else {
     // ============================== epilogue: store Y2, accumulate its column sums ==============================
-    const int q = warp & 3;
-    float* st = staging + q * (32 * 36);
-    double s1[C::NB], s2[C::NB];
+    constexpr int NBW = C::NB / 2;                       // column blocks per warp
+    const int ew = warp - kFwdProducerWarps;             // 0..7
+    const int q = warp & 3, half = ew >> 2;              // TMEM lane quarter; parity of the blocks this warp handles
+    float* st = staging + ew * (32 * 32);
+    // fp32 partial sums per block, folded into doubles every 8 tiles (DADD is slow on this part)
+    float ps1[NBW], ps2[NBW];
+    double d1[NBW], d2[NBW];
 #pragma unroll
-    for (int b = 0; b < C::NB; ++b) s1[b] = s2[b] = 0.0;
+    for (int b = 0; b < NBW; ++b) {
+      ps1[b] = ps2[b] = 0.f;
+      d1[b] = d2[b] = 0.0;
+    }
     uint32_t tcount = 0;
-    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+    const int ch = lane & 7, rsub = lane >> 3;
     for (int t = t0; t < t1; ++t, ++tcount) {
       const int ib = t / p.g.tiles_j, jb = t - ib * p.g.tiles_j;
       const int acc = tcount & 1;
@@ -325,46 +356,68 @@ __global__ void __launch_bounds__(kThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
       mbar_wait(smem_u32(&bars.tfull[acc]), acc_ph);
       tc_fence_after();
 #pragma unroll
-      for (int b = 0; b < C::NB; ++b) {
+      for (int bi = 0; bi < NBW; ++bi) {
+        const int b = 2 * bi + half;
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + b * 32), r);
         tmem_ld_wait();
-        stage_block(st, lane, r);
+        // dense 32 x 32 tile, 16-byte chunk j of row u stored at chunk j ^ (u & 7): conflict-free for the row writes
+        // (thread = row), the column reads (lane = column) and the row reads of the coalesced store
+#pragma unroll
+        for (int jc = 0; jc < 8; ++jc)
+          *reinterpret_cast<float4*>(st + lane * 32 + ((jc ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(r[4 * jc]), __uint_as_float(r[4 * jc + 1]), __uint_as_float(r[4 * jc + 2]),
+                          __uint_as_float(r[4 * jc + 3]));
         __syncwarp();
         // rows outside the slice were generated as zeros, so they add nothing to the sums
         float a1 = 0.f, a2 = 0.f;
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
-          const float x = st[u * 36 + lane];
+          const float x = st[u * 32 + ((((lane >> 2) ^ (u & 7)) << 2) | (lane & 3))];
           a1 += x;
           a2 = fmaf(x, x, a2);
         }
-        s1[b] += (double)a1;
-        s2[b] += (double)a2;
+        ps1[bi] += a1;
+        ps2[bi] += a2;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int u = q * 32 + rsub + 4 * k;
+          const int row = rsub + 4 * k, u = q * 32 + row;
           const int li = ib * BI + (u >> 3), j = jb * BJ + (u & 7);
           if (li < p.g.n_i && j < p.g.n)
-            *reinterpret_cast<float4*>(p.Y2 + ((int64_t)li * p.g.n + j) * H + b * 32 + c4) =
-                *reinterpret_cast<const float4*>(st + (rsub + 4 * k) * 36 + c4);
+            *reinterpret_cast<float4*>(p.Y2 + ((int64_t)li * p.g.n + j) * H + b * 32 + ch * 4) =
+                *reinterpret_cast<const float4*>(st + row * 32 + ((ch ^ (row & 7)) << 2));
         }
         __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&bars.tempty[acc]));
-    }
-    // column sums: the four lane quarters are combined through shared memory, one double atomic per column and CTA
-    double* red = reinterpret_cast<double*>(staging);      // [4][2H] doubles = 16 KB <= the 18 KB of staging tiles
-    named_bar_sync(1, kEpiThreads);
+      if ((tcount & 7) == 7) {
 #pragma unroll
-    for (int b = 0; b < C::NB; ++b) {
-      red[q * 2 * H + b * 32 + lane] = s1[b];
-      red[q * 2 * H + H + b * 32 + lane] = s2[b];
+        for (int b = 0; b < NBW; ++b) {
+          d1[b] += (double)ps1[b];
+          d2[b] += (double)ps2[b];
+          ps1[b] = ps2[b] = 0.f;
+        }
+      }
     }
-    named_bar_sync(1, kEpiThreads);
-    for (int idx = q * 32 + lane; idx < 2 * H; idx += kEpiThreads)
-      atomicAdd(p.stats + idx, red[idx] + red[2 * H + idx] + red[4 * H + idx] + red[6 * H + idx]);
+    // column sums: the four lane quarters of each block parity are combined through shared memory, one double atomic
+    // per column, statistic and CTA
+    double* red = reinterpret_cast<double*>(staging);     // [8 warps][NBW][2][32] doubles = 16 KB of the 32 KB tiles
+    named_bar_sync(1, kFwdEpiWarps * 32);
+#pragma unroll
+    for (int b = 0; b < NBW; ++b) {
+      red[((ew * NBW + b) * 2 + 0) * 32 + lane] = d1[b] + (double)ps1[b];
+      red[((ew * NBW + b) * 2 + 1) * 32 + lane] = d2[b] + (double)ps2[b];
+    }
+    named_bar_sync(1, kFwdEpiWarps * 32);
+    for (int idx = ew * 32 + lane; idx < 2 * H; idx += kFwdEpiWarps * 32) {
+      const int stat = idx / H, col = idx % H;
+      const int b = col >> 5, l = col & 31;
+      double v = 0.0;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) v += red[((((b & 1) * 4 + qq) * NBW + (b >> 1)) * 2 + stat) * 32 + l];
+      atomicAdd(p.stats + idx, v);
+    }
   }
 
   tc_fence_before();
@@ -560,8 +613,8 @@ pge_l2_bwd_dx_kernel(const __grid_constant__ CUtensorMap map_y2, BwdParams p) {
           for (int jj = 0; jj < BJ; ++jj) pa[jj] = __ldg(pa_base + (int64_t)(jj < nj ? jj : 0) * H + c);
 #pragma unroll
           for (int k = 0; k < 4; ++k) pb[k] = (ni > 0) ? __ldg(pb_base + (int64_t)(k < ni ? k : 0) * H + c) : 0.f;
-          const float mu = __ldg(p.bn1.mean + c + lane), rs = __ldg(p.bn1.rstd + c + lane),
-                      g = __ldg(p.bn1.gamma + c + lane), bt = __ldg(p.bn1.beta + c + lane);
+          const float grs = __ldg(p.bn1.gamma + c + lane) * __ldg(p.bn1.rstd + c + lane);
+          const float off = fmaf(-__ldg(p.bn1.mean + c + lane), grs, __ldg(p.bn1.beta + c + lane));
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + c), r);
           tmem_ld_wait();
@@ -576,7 +629,7 @@ pge_l2_bwd_dx_kernel(const __grid_constant__ CUtensorMap map_y2, BwdParams p) {
 #pragma unroll
             for (int jj = 0; jj < BJ; ++jj) {
               float x = st[(k * 8 + jj) * 36 + lane];
-              x = (fmaf(g, (pa[jj] + pb[k] - mu) * rs, bt) > 0.f) ? x : 0.f;
+              x = (h1_pre(pa[jj], pb[k], grs, off) > 0.f) ? x : 0.f;
               gsum += x;
               ga[jj] += x;
             }
@@ -624,8 +677,8 @@ struct DwCfg {
   static constexpr uint32_t kTmemCols = MH * H;           // 512 (H = 256) / 128 (H = 128)
   static constexpr uint32_t kIdesc = make_idesc_bf16(128, H, 1, 1);
   static constexpr int F4 = H / 4;                        // float4 per row
-  static constexpr int kRowStep = 128 / F4;               // rows covered by one pass of a 128-thread producer group
-  static constexpr int kIters = DW_ROWS / kRowStep;       // 16 (H = 256) / 8 (H = 128)
+  static constexpr int kRowStep = 256 / F4;               // rows covered by one pass of the 256 producer threads
+  static constexpr int kIters = DW_ROWS / kRowStep;       // 8 (H = 256) / 4 (H = 128)
 };
 
 template <int H, int NPASS>
@@ -650,92 +703,71 @@ pge_l2_bwd_dw_kernel(const __grid_constant__ CUtensorMap map_y2, BwdParams p) {
   const uint32_t tmem_base = bars.tmem_holder;
 
   if (warp < kProducerWarps) {
-    const bool group_a = warp < 4;                         // warps 0-3: dY2 (in place), warps 4-7: H1 (generated)
-    const int tg = threadIdx.x & 127;
-    const int c16 = tg % C::F4, rbase = tg / C::F4;
+    // all 8 warps produce both operands of a k-stage (32 pair rows x H): thread = (float4 column c16, row residue
+    // rbase), rows r = rbase + kRowStep i.  A warp covers whole (row, column half) pairs, so the raw Y2 bytes it reads
+    // are exactly the ones it overwrites with the dY2 operand (in place); H1 is generated into the second region.
+    const int tid = threadIdx.x;
+    const int c16 = tid % C::F4, rbase = tid / C::F4;
     const int c = c16 * 4, cb = c16 >> 4, c4 = c16 & 15;
+    constexpr int JJ = BJ / C::kRowStep;                  // distinct jl per thread; il = i / JJ
+    const Dy2Consts k2 = load_dy2_consts(p.bn2, p.w3, p.s1, p.s2, p.inv_count, c);
+    const H1Consts k1 = load_h1_consts(p.bn1, c);
     uint32_t it = 0;
-    if (group_a) {
-      const Dy2Consts k = load_dy2_consts(p.bn2, p.w3, p.s1, p.s2, p.inv_count, c);
-      for (int t = t0; t < t1; ++t, ++it) {
-        const int ib = t / p.g.tiles_j, jb = t - ib * p.g.tiles_j;
-        const int s = it % kDwStages;
-        const uint32_t ph = (it / kDwStages) & 1;
-        uint8_t* op = smem + s * C::kStageBytes;
-        // raw box x (32 columns) sits at x * 4 KB: even boxes alias the hi plane of sub-tile x / 2, odd boxes its lo plane
-        const uint8_t* raw = op + (2 * cb + (c4 >> 3)) * (DW_ROWS * 128) + (c4 & 7) * 16;
-        uint8_t* hi = op + cb * C::kSub;
-        uint8_t* lo = hi + DW_ROWS * 128;
-        bool waited = false;
-#pragma unroll 1
-        for (int half = 0; half < C::kIters; half += 8) {
-          float de[8];
-          uint32_t vmask = 0;
+    for (int t = t0; t < t1; ++t, ++it) {
+      const int ib = t / p.g.tiles_j, jb = t - ib * p.g.tiles_j;
+      const int s = it % kDwStages;
+      const uint32_t ph = (it / kDwStages) & 1;
+      uint8_t* op = smem + s * C::kStageBytes;
+      // raw box x (32 columns) sits at x * 4 KB: even boxes alias the hi plane of sub-tile x / 2, odd boxes its lo plane
+      const uint8_t* raw = op + (2 * cb + (c4 >> 3)) * (DW_ROWS * 128) + (c4 & 7) * 16;
+      uint8_t* hi_a = op + cb * C::kSub;
+      uint8_t* hi_b = hi_a + C::kOperand;
+      float de[C::kIters];
+      uint32_t vmask = 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rbase + C::kRowStep * (half + i);
-            const int li = ib * DW_BI + (r >> 3), j = jb * BJ + (r & 7);
-            const bool valid = li < p.g.n_i && j < p.g.n;
-            de[i] = valid ? __ldg(p.dE + (int64_t)li * p.g.n + j) : 0.f;
-            vmask |= (valid ? 1u : 0u) << i;
-          }
-          if (!waited) {
-            mbar_wait(smem_u32(&bars.raw[s]), ph);
-            waited = true;
-          }
-          float4 y[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            y[i] = *reinterpret_cast<const float4*>(raw + (rbase + C::kRowStep * (half + i)) * 128);
-          __syncwarp();          // a warp owns (row, column half) pairs exclusively: reads complete before the overwrite
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rbase + C::kRowStep * (half + i);
-            float4 o = dy2_value4(y[i], de[i], k);
-            if (!((vmask >> i) & 1u)) o = make_float4(0.f, 0.f, 0.f, 0.f);
-            store_split4<C::kWithLo>(hi, lo, sw128_offset(r, c4 * 4), o);
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars.full[s]));
+      for (int i = 0; i < C::kIters; ++i) {
+        const int r = rbase + C::kRowStep * i;
+        const int li = ib * DW_BI + (r >> 3), j = jb * BJ + (r & 7);
+        const bool valid = li < p.g.n_i && j < p.g.n;
+        de[i] = valid ? __ldg(p.dE + (int64_t)li * p.g.n + j) : 0.f;
+        vmask |= (valid ? 1u : 0u) << i;
       }
-    } else {
-      const float4 mu = ld4(p.bn1.mean + c), rs = ld4(p.bn1.rstd + c), g = ld4(p.bn1.gamma + c), b = ld4(p.bn1.beta + c);
-      for (int t = t0; t < t1; ++t, ++it) {
-        const int ib = t / p.g.tiles_j, jb = t - ib * p.g.tiles_j;
-        const int s = it % kDwStages;
-        const uint32_t ph = (it / kDwStages) & 1;
-        uint8_t* hi = smem + s * C::kStageBytes + C::kOperand + cb * C::kSub;
-        uint8_t* lo = hi + DW_ROWS * 128;
-        // rows r = rbase + kRowStep * i: jl = r & 7 takes JJ = 8 / kRowStep distinct values, il = r >> 3 takes DW_BI
-        constexpr int JJ = BJ / C::kRowStep;
-        float4 pb[DW_BI], pa[JJ];
+      float4 pb[DW_BI], pa[JJ];
 #pragma unroll
-        for (int il = 0; il < DW_BI; ++il) {
-          const int li = ib * DW_BI + il;
-          pb[il] = ld4(p.Pb + (int64_t)(p.g.i_first + (li < p.g.n_i ? li : 0)) * H + c);
-        }
+      for (int il = 0; il < DW_BI; ++il) {
+        const int li = ib * DW_BI + il;
+        pb[il] = ld4(p.Pb + (int64_t)(p.g.i_first + (li < p.g.n_i ? li : 0)) * H + c);
+      }
 #pragma unroll
-        for (int jj = 0; jj < JJ; ++jj) {
-          const int j = jb * BJ + rbase + C::kRowStep * jj;
-          pa[jj] = ld4(p.Pa + (int64_t)(j < p.g.n ? j : 0) * H + c);
-        }
-        mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1);
+      for (int jj = 0; jj < JJ; ++jj) {
+        const int j = jb * BJ + rbase + C::kRowStep * jj;
+        pa[jj] = ld4(p.Pa + (int64_t)(j < p.g.n ? j : 0) * H + c);
+      }
+      mbar_wait(smem_u32(&bars.raw[s]), ph);       // the TMA was issued after the stage was released: both regions are free
+      {
+        float4 y[C::kIters];
+#pragma unroll
+        for (int i = 0; i < C::kIters; ++i)
+          y[i] = *reinterpret_cast<const float4*>(raw + (rbase + C::kRowStep * i) * 128);
+        __syncwarp();            // reads complete before the overwrite
 #pragma unroll
         for (int i = 0; i < C::kIters; ++i) {
           const int r = rbase + C::kRowStep * i;
-          const int il = i / JJ, jj = i % JJ;                 // r >> 3 and (r & 7 - rbase) / kRowStep
-          const int li = ib * DW_BI + il, j = jb * BJ + (r & 7);
-          const bool valid = li < p.g.n_i && j < p.g.n;
-          float4 o = h1_value4(pa[jj], pb[il], mu, rs, g, b);
-          if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
-          store_split4<C::kWithLo>(hi, lo, sw128_offset(r, c4 * 4), o);
+          float4 o = dy2_value4(y[i], de[i], k2);
+          if (!((vmask >> i) & 1u)) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          store_split4<C::kWithLo>(hi_a, hi_a + DW_ROWS * 128, sw128_offset(r, c4 * 4), o);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars.full[s]));
       }
+#pragma unroll
+      for (int i = 0; i < C::kIters; ++i) {
+        const int r = rbase + C::kRowStep * i;
+        float4 o = h1_value4(pa[i % JJ], pb[i / JJ], k1);
+        if (!((vmask >> i) & 1u)) o = make_float4(0.f, 0.f, 0.f, 0.f);
+        store_split4<C::kWithLo>(hi_b, hi_b + DW_ROWS * 128, sw128_offset(r, c4 * 4), o);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars.full[s]));
     }
   } else if (warp == kTmaWarp) {
     if (lane == 0) {
@@ -927,7 +959,7 @@ static int pack_image(const float* W, int64_t ldw, int h, int trans, int planes,
 template <int H, int NPASS>
 static int launch_fwd(FwdParams& p, cudaStream_t st) {
   using C = Cfg<H, NPASS>;
-  constexpr size_t smem = (size_t)C::kStages * C::kStageBytes + kStagingBytes + 1024;
+  constexpr size_t smem = (size_t)C::kStages * C::kStageBytes + kFwdStagingBytes + 1024;
   static bool configured = false;
   if (!configured) {
     const int rc = set_smem(pge_l2_fwd_kernel<H, NPASS>, smem, "cudaFuncSetAttribute(pge_l2_fwd)");

@@ -32,6 +32,8 @@ class GCond(GCondBase):
         self._prepare_real()                                  # to_tensor + normalize_adj_tensor(sparse=True)
         feat_init = self.init()
         self.feat_syn.copy_(feat_init.to(K.device))
+        if self.trace:
+            self.trace("feat_init", feat=feat_init, ids=self.init_ids)
         self.layout = _engine.ClassLayout(K, self.labels_syn, data.nclass, owned=getattr(self, "owned_classes", None))
         self.model = _engine.build_model(K, args.condense_model, self.d, args.hidden, data.nclass, args.nlayers,
                                          args.ntrans, self.layout, identity_adj=self.x_variant)
@@ -84,6 +86,8 @@ class GCond(GCondBase):
                         # same features, same batch statistics); its activations were kept for the backward below
                         self.adj_syn, r_norm = self._pge_ready
                         self._pge_ready = None
+            if self.trace and not self.x_variant:
+                self.trace("adj_syn", step=(it, ol), adj=self.adj_syn)
             loss, dX, dA, rb = self.match_step(model)
             with K.timed("phase_allreduce"):
                 loss, dX, dA = self.reduce_partials(loss, dX, dA)     # class sharding: one all-reduce per outer step

@@ -27,9 +27,12 @@ class TransAndInd:
         self.edge_index = data.edge_index
         if dataset in ("flickr", "reddit", "ogbn-arxiv"):
             from sklearn.preprocessing import StandardScaler     # loader.py:113-119
+            # torch tensors go to sklearn exactly as the reference passes them: check_array turns them into float64, so
+            # the standardisation is computed in double and rounded to fp32 once (a float32 ndarray would be
+            # transformed in place in fp32 and differ from the reference in the last bit)
             scaler = StandardScaler()
-            scaler.fit(self.x[data.idx_train].numpy())
-            self.feat_full = torch.from_numpy(scaler.transform(self.x.numpy())).float()
+            scaler.fit(self.x[data.idx_train])
+            self.feat_full = torch.from_numpy(scaler.transform(self.x)).float()
         if norm and dataset in ("cora", "citeseer", "pubmed"):
             self.feat_full = F.normalize(self.feat_full, p=1, dim=1)
         self.idx_train, self.idx_val, self.idx_test = data.idx_train, data.idx_val, data.idx_test

@@ -88,6 +88,10 @@ def run_case(name, epochs=None, device="cpu", **extra):
                 seen["grads"][step] = (kw["feat_grad"].cpu().numpy().copy()[:, ::sub], flat)
         elif kind == "model_init":
             seen["model_init"].append(np.concatenate([w.cpu().numpy().ravel() for w in kw["W"]])[::sub])
+        elif kind == "feat_init":
+            seen["feat_init"] = kw["feat"].cpu().numpy().copy()
+        elif kind == "adj_syn" and "adj_syn0" not in seen:
+            seen["adj_syn0"] = kw["adj"].cpu().numpy().copy()
 
     helpers.seed_everything(args.seed)
     agent = create_reducer(args.method, setting=args.setting, data=data, args=args)
@@ -119,6 +123,13 @@ def check_against_golden(gold, sub, args, data, agent, seen, pge_init, first_tol
             assert np.array_equal(bval, gold[f"s0_c{c}_h{h}_val"])
     got_init = np.stack(seen["model_init"])
     assert np.array_equal(got_init, gold["model_init"][:len(got_init)])
+    # Random init (gcond_base.py:117-151 -> sparsification/random.py): the selected rows, bit exact
+    assert np.array_equal(seen["feat_init"][:, ::sub], gold["feat_init"])
+    if "adj_syn0" in seen and "adj_syn_norm0" in gold.files:
+        # first normalised synthetic adjacency dense_gcn_norm(pge(feat_syn)) (gcond.py:48-49)
+        a0, r0 = seen["adj_syn0"], gold["adj_syn_norm0"]
+        np.testing.assert_allclose(a0[::sub, ::sub] if r0.shape != a0.shape else a0, r0, rtol=first_tol,
+                                   atol=first_tol * np.abs(r0).max())
     # ---- floating point
     losses = np.array(seen["losses"])
     n = len(losses)

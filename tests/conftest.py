@@ -24,3 +24,19 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """The parity suites leave the errors they measured in gpurun_out/ (copied to profiles/ by hand)."""
+    try:
+        from tests.test_engine_emulated import MEASURED
+    except Exception:
+        return
+    if not MEASURED:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    rows = [dict(method=k[0], dataset=k[1], device=k[2], precision=k[3], steps=k[4], **v) for k, v in MEASURED.items()]
+    with open(os.path.join(out, "parity_fixture_errors.json"), "w") as f:
+        json.dump(rows, f, indent=1)

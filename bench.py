@@ -34,6 +34,18 @@ WORKLOADS = {
 }
 
 
+def config_dict(workload, n_gpus):
+    """The `config` object: identical in both arms (same keys, same values) for a given workload and GPU count."""
+    par = "single GPU" if n_gpus <= 1 else f"classes sharded x{n_gpus} + PGE pair rows sharded"
+    return {"workload": WORKLOADS[workload],
+            "step": "one condensation epoch = outer_loop gradient-matching steps, each with its inner loop "
+                    "(gcond.py:40-74), checkpoints disabled; the reference arm times single outer steps of the same "
+                    "loop on the host cores and extrapolates to an epoch",
+            "parallelism": par,
+            "l2": "inputs exceed L2: per epoch the PGE streams N'^2 x h fp32 activations (846 MB at the arxiv shape) "
+                  "and freshly sampled blocks through HBM; no explicit flush needed"}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -137,18 +149,80 @@ def time_oracle(workload, outer_steps, warm_steps=0):
     return eps, per, torch.get_num_threads(), desc
 
 
+def time_reference_real(workload, outer_steps, warm_steps=0, budget_s=150.0):
+    """The UNMODIFIED reference (staged by oracle/stage_ref.py into oracle/_ref) through its own public API:
+    create_reducer('gcond', ...).reduce(data) on the host cores, gpu_id = -1, with the third-party wheels replaced by the
+    CPU stand-ins of oracle/ref_shim.  One outer step = the span between two consecutive optimiser steps of
+    gcond.py:58-61 (inner loop of step s + matching of step s+1).  Stops after `outer_steps` timed steps or, once two
+    steps are in, after `budget_s` seconds.  Returns (epochs/s, s per outer step, cores, description, steps timed)."""
+    import tempfile
+    import torch
+    from oracle import stage_ref
+    os.environ["GRAPHSLIM_REFERENCE_ROOT"] = stage_ref.REF_DIR
+    from oracle import ref_shim
+    ref_shim.install()
+    from oracle import make_goldens as MG
+    from graphslim.reduction import create_reducer
+    from graphslim.utils import seed_everything as ref_seed
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    case = dict(dataset=workload, method="gcond", epochs=1, graph=dict(name=workload, seed=0), overrides={})
+    if workload == "flickr":
+        case["overrides"]["condense_model"] = "GCN"          # BASELINE.json configs[2]
+    args = MG.reference_args(case, tempfile.mkdtemp(prefix="gs_ref_bench_"))
+    per_epoch, inner = int(args.outer_loop), int(args.inner_loop)
+    args.outer_loop = warm_steps + outer_steps + 1           # stamps bracket steps: one more optimiser call than steps
+    data = MG.build_reference_data(case, args)
+    ref_seed(args.seed)
+    agent = create_reducer(args.method, setting=args.setting, data=data, args=args)
+    stamps = []
+
+    class _Enough(Exception):
+        pass
+
+    def spy(step_fn):
+        def wrapped(*a, **k):
+            out = step_fn(*a, **k)
+            stamps.append(time.perf_counter())
+            timed = len(stamps) - 1 - warm_steps
+            if timed >= outer_steps or (timed >= 2 and stamps[-1] - stamps[warm_steps] > budget_s):
+                raise _Enough()
+            return out
+        return wrapped
+
+    agent.optimizer_feat.step = spy(agent.optimizer_feat.step)
+    agent.optimizer_pge.step = spy(agent.optimizer_pge.step)
+    try:
+        agent.reduce(data, verbose=False)
+    except _Enough:
+        pass
+    timed = len(stamps) - 1 - warm_steps
+    per = (stamps[-1] - stamps[warm_steps]) / timed
+    desc = (f"{timed} outer step(s) of epoch 0 of the unmodified reference (graphslim.condensation.gcond.GCond.reduce, "
+            f"gpu_id=-1; {per_epoch} outer steps per epoch, each incl. {inner} inner step(s) and neighbour sampling) "
+            f"after {warm_steps} warm-up, extrapolated to one epoch; torch_sparse / PyG replaced by the CPU stand-ins "
+            f"of oracle/ref_shim")
+    return 1.0 / (per * per_epoch), per, torch.get_num_threads(), desc, timed
+
+
 def run_reference(ns):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    eps, per, cores, desc = time_oracle(ns.workload, ns.steps, ns.warmup)
+    from oracle import stage_ref
+    if stage_ref.stage() is not None and not ns.port:
+        eps, per, cores, desc, timed = time_reference_real(ns.workload, ns.steps, ns.warmup)
+        kind = "reference"
+    else:
+        eps, per, cores, desc = time_oracle(ns.workload, ns.steps, ns.warmup)
+        kind, timed = "port", ns.steps
     line = {
         "impl": "reference", "metric": "gcond_condensation_epochs_per_sec", "value": eps, "unit": "epochs/s",
-        "n_gpus": ns.gpus, "steps": ns.steps, "warmup": ns.warmup, "ms_per_step": per * 1e3,
+        "n_gpus": ns.gpus, "steps": ns.steps, "warmup": ns.warmup, "ms_per_step": 1e3 / eps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[ns.workload], "step": "one outer step of the reference loop on CPU; value "
-                   "is extrapolated to epochs/s (outer_loop steps per epoch)"},
-        "cpu_baseline": {"value": eps, "unit": "epochs/s", "cores": cores, "kind": "port", "sample": desc},
+        "config": config_dict(ns.workload, ns.gpus),
+        "cpu_baseline": {"value": eps, "unit": "epochs/s", "cores": cores, "kind": kind, "sample": desc,
+                         "seconds_per_outer_step": per, "outer_steps_timed": timed},
         "e2e": {"value": eps, "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -228,6 +302,46 @@ def spmm_sharded_probe(agent, world, rank, single_ms, iters=10):
             "l2_flushed": True}
 
 
+def quick_epochs(workload, precision, steps, warmup, world, rank, local):
+    """Device-timed epochs of another workload / precision inside the same run (inputs resident, CUDA events, barrier +
+    synchronize on both sides, max over ranks): the secondary lines of the JSON (`precision0`, `reddit`)."""
+    import torch
+    import torch.distributed as dist
+    from graphslim_b200.reduction import create_reducer
+    raw, args, gdata = make_problem(workload, local, epochs=steps + warmup, gemm_precision=precision, track_loss=False)
+    data = gdata.TransAndInd(raw, args.dataset, args.pre_norm)
+    seed_everything(args.seed)
+    if world > 1:
+        from graphslim_b200 import parallel
+        agent = parallel.SHARDED[args.method](args.setting, data, args)
+    else:
+        agent = create_reducer(args.method, setting=args.setting, data=data, args=args)
+    agent.setup(data)
+    for it in range(warmup):
+        agent.run_epoch(it)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for it in range(warmup, warmup + steps):
+        agent.run_epoch(it)
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_syn = int(agent.nnodes_syn)
+    del agent, data, raw
+    torch.cuda.empty_cache()
+    return {"workload": WORKLOADS[workload], "gemm_precision": precision, "value": steps / (ms / 1e3), "unit": "epochs/s",
+            "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "n_gpus": world, "n_syn": n_syn}
+
+
 def run_ours(ns):
     import numpy as np
     import torch
@@ -300,47 +414,63 @@ def run_ours(ns):
     value = K_ / (ms / 1e3)
     sample_bytes_per_epoch = (getattr(agent.sampler, "bytes_moved", 0) - h2d0) / max(K_, 1)
 
-    # ---- roofline of the dominant kernel (PGE layer-2 product), measured live above ------------
-    # The N'^2 x h x h product streams its fp32 A operand (N'^2 x h) in and its fp32 output out exactly once: at
-    # h = 256 that is 64 flop/byte, below the bf16 ridge (sustained TF/s / HBM GB/s = ~210 flop/byte, ~70 with the
-    # three MMA passes of the 3xBF16 split), so the binding roofline is HBM; the tensor-pipe figures are kept beside it.
+    # ---- rooflines of the three N'^2-deep PGE products, measured live above (CUDA events on the launch stream) ----
+    # the PGE layer-2 contractions are judged on the TENSOR roofline: achieved = algorithmic flops
+    # (2 N'^2 h^2 per product, whatever number of BF16 passes the precision mode spends on them) / event time, against
+    # the measured sustained bf16 peak.  The HBM view (algorithmic bytes: the one N'^2 x h array each kernel must stream)
+    # and the MMA-work view (flops x passes) are kept beside it; `traffic` is the ncu DRAM byte count of one launch.
     n_syn, h = agent.nnodes_syn, agent.pge.h
     pge_sharded = bool(getattr(agent, "pge_sharded", False))
-    roof = None
-    if "pge_l2_fwd" in kernel_times and kernel_times["pge_l2_fwd"][0] > 0:
-        cnt, tot = kernel_times["pge_l2_fwd"]
-        pair_rows = n_syn * n_syn
-        sh = getattr(agent.pge, "shard", None)
-        if sh is not None:                                   # PGE pair rows dealt to the ranks: this rank's share
-            pair_rows = sh["rows"][sh["rank"]]
-        flops = 2.0 * pair_rows * h * h
-        alg_bytes = 4.0 * pair_rows * h * 2 + 4.0 * h * h
+    pair_rows = n_syn * n_syn
+    sh = getattr(agent.pge, "shard", None)
+    if sh is not None:                                   # PGE pair rows dealt to the ranks: this rank's share
+        pair_rows = sh["rows"][sh["rank"]]
+    fused = agent.K.pge_fused_supported(h, agent.pge.nchunks)
+    passes = {0: 1, 1: 3, 2: 1}[ns.precision]
+    traffic_all = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        traffic_all = json.load(open(tpath)).get(ns.workload, {})
+    big = 4.0 * pair_rows * h                                # one N'^2 x h fp32 array
+    small = 8.0 * n_syn * h + 4.0 * h * h
+    specs = {
+        "pge_l2_fwd": ("PGE layer-2 forward Y2 = relu(bn1(Pa[j]+Pb[i])) W2^T: " +
+                       ("pge_l2_fwd_kernel (H1 generated in the producer, BN2 sums in the epilogue)" if fused else
+                        "gs_gemm_f32 on a materialised H1"), (big if fused else 2 * big) + small),
+        "pge_l2_bwd_dx": ("PGE backward dH1 = dY2 W2: " +
+                          ("pge_l2_bwd_dx_kernel (dY2 from TMA-loaded Y2 tiles, masked reduction in the epilogue)"
+                           if fused else "gs_gemm_f32 on materialised dY2 -> dH1"),
+                          (big if fused else 2 * big) + small + 4.0 * pair_rows),
+        "pge_l2_bwd_dw": ("PGE backward dW2 = dY2^T H1 (K = N'^2): " +
+                          ("pge_l2_bwd_dw_kernel (both operands produced on chip, MN-major UMMA, result in TMEM)"
+                           if fused else "gs_gemm_f32 on materialised dY2, H1"),
+                          (big if fused else 2 * big) + small + 4.0 * pair_rows),
+    }
+    flops = 2.0 * pair_rows * h * h
+    rooflines = []
+    for tag, (kname, alg_bytes) in specs.items():
+        if tag not in kernel_times or kernel_times[tag][0] == 0:
+            continue
+        cnt, tot = kernel_times[tag]
         sec = tot / cnt / 1e3
-        ach_tf = flops / sec / 1e12
-        ach_gb = alg_bytes / sec / 1e9
-        passes = {0: None, 1: 3, 2: 1}[ns.precision]
-        t_hbm, t_tc = alg_bytes / (pk["hbm"] * 1e9), flops * (passes or 1) / (pk["tf_sustained"] * 1e12)
-        share = {k: v[1] / ms for k, v in kernel_times.items()}
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath) and world == 1:
-            traffic = json.load(open(tpath)).get(ns.workload, {}).get("pge_l2_fwd")
-        roof = {"kernel": "PGE layer-2 product (N'^2 x h x h) forward, gs_gemm_f32 precision=%d (gemm_tc_kernel)"
-                          % ns.precision,
-                "bound": "hbm" if t_hbm >= t_tc else "tensor",
-                "achieved": ach_gb if t_hbm >= t_tc else ach_tf,
-                "peak": pk["hbm"] if t_hbm >= t_tc else pk["tf_sustained"],
-                "unit": "GB/s" if t_hbm >= t_tc else "TFLOP/s",
-                "frac": (ach_gb / pk["hbm"]) if t_hbm >= t_tc else (ach_tf / pk["tf_sustained"]),
-                "traffic": (traffic or {}).get("dram_bytes_per_launch"),
-                "traffic_source": (traffic or {}).get("source"),
-                "peak_source": pk["source"] + (", copy bandwidth" if t_hbm >= t_tc else ", sustained bf16"),
-                "launches": cnt, "avg_ms": tot / cnt, "alg_bytes_per_launch": alg_bytes, "flops_per_launch": flops,
-                "roofline_ms": {"hbm": t_hbm * 1e3, "tensor": t_tc * 1e3},
-                "tensor": {"achieved_TFLOPs_algorithmic": ach_tf, "mma_passes": passes,
-                           "frac_of_sustained_bf16_algorithmic": ach_tf / pk["tf_sustained"],
-                           "frac_of_sustained_bf16_mma_work": ach_tf * (passes or 1) / pk["tf_sustained"]},
-                "share_of_step": share}
+        ach_tf, ach_gb = flops / sec / 1e12, alg_bytes / sec / 1e9
+        tr = traffic_all.get(tag) or {}
+        rooflines.append({
+            "kernel": kname, "tag": tag, "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sustained"],
+            "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sustained"],
+            "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+            "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+            "launches": cnt, "avg_ms": tot / cnt, "share_of_step": tot / ms,
+            "flops_per_launch": flops, "alg_bytes_per_launch": alg_bytes, "mma_passes": passes,
+            "mma_work_frac_of_sustained_bf16": ach_tf * passes / pk["tf_sustained"],
+            "hbm": {"achieved_GBps": ach_gb, "peak_GBps": pk["hbm"], "frac": ach_gb / pk["hbm"]},
+            "roofline_ms": {"tensor_algorithmic": flops / (pk["tf_sustained"] * 1e12) * 1e3,
+                            "tensor_mma_work": flops * passes / (pk["tf_sustained"] * 1e12) * 1e3,
+                            "hbm": alg_bytes / (pk["hbm"] * 1e9) * 1e3}})
+    rooflines.sort(key=lambda r: -r["share_of_step"])
+    roof = dict(rooflines[0]) if rooflines else None          # the tagged kernel with the largest share of the step
+    if roof is not None:
+        roof["share_of_step_all"] = {k: v[1] / ms for k, v in kernel_times.items()}
     spmm = spmm_probe(agent, pk) if rank == 0 else None
     spmm_sharded = None
     if world > 1:
@@ -375,14 +505,33 @@ def run_ours(ns):
            "note": "GCond(...).reduce(data) on host tensors: graph+features H2D, normalisation, init, K epochs "
                    "(each streaming sampled blocks H2D), result D2H; one-off setup amortised over K epochs"}
 
+    # ---- secondary lines measured in the same run ----------------------------------------------------
+    del e2e_agent, out
+    torch.cuda.empty_cache()
+    extra = {}
+    if not ns.no_extra:
+        if world == 1 and ns.precision != 0:
+            # the all-fp32-FMA mode (north-star 1e-4 bound) next to the tensor-core mode of the headline
+            extra["precision0"] = quick_epochs(ns.workload, 0, 2, 1, world, rank, local)
+        if ns.workload != "reddit":
+            # BASELINE.json quotes the multi-GPU target on the Reddit shape: emitted at every N so the driver's
+            # 1/2/4/8 runs carry both curves
+            extra["reddit"] = quick_epochs("reddit", ns.precision, 5, 3, world, rank, local)
     if rank != 0:
         return
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------
     cpu = None
     if world == 1 and not ns.no_cpu_baseline:
         n_steps = {"cora": 20, "ogbn-arxiv": 2, "flickr": 3, "reddit": 2}[ns.workload]
-        eps, per, cores, desc = time_oracle(ns.workload, n_steps, 0)
-        cpu = {"value": eps, "unit": "epochs/s", "cores": cores, "kind": "port", "sample": desc,
+        from oracle import stage_ref
+        if stage_ref.stage() is not None and ns.workload != "reddit":
+            # the unmodified reference through its own API (oracle/_ref + oracle/ref_shim), a bounded sample
+            eps, per, cores, desc, _ = time_reference_real(ns.workload, n_steps, 0, budget_s=40.0)
+            kind = "reference"
+        else:
+            eps, per, cores, desc = time_oracle(ns.workload, n_steps, 0)
+            kind = "port"
+        cpu = {"value": eps, "unit": "epochs/s", "cores": cores, "kind": kind, "sample": desc,
                "seconds_per_outer_step": per}
     line = {
         "metric": "gcond_condensation_epochs_per_sec", "value": value, "unit": "epochs/s", "n_gpus": world,
@@ -390,13 +539,11 @@ def run_ours(ns):
         "vs_baseline": None, "dtype": "f32" if ns.precision == 0 else ("bf16x3-split/f32-accum" if ns.precision == 1
                                                                          else "bf16/f32-accum"),
         "data": "synthetic",
-        "config": {"workload": WORKLOADS[ns.workload],
-                   "parallelism": (f"classes sharded x{world}" + (" + PGE pair rows sharded" if pge_sharded else ""))
-                   if world > 1 else "single GPU", "gemm_precision": ns.precision,
-                   "l2": "inputs exceed L2: per epoch the PGE streams N'^2 x h fp32 activations (>800 MB at the "
-                         "arxiv shape) and freshly sampled blocks through HBM; no explicit flush needed",
-                   "sampled_block_bytes_per_epoch": int(sample_bytes_per_epoch)},
-        "roofline": roof, "spmm": spmm, "spmm_sharded": spmm_sharded, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+        "config": config_dict(ns.workload, world),
+        "gemm_precision": ns.precision, "pge_fused": bool(fused), "pge_pair_rows_sharded": pge_sharded,
+        "sampled_block_bytes_per_epoch": int(sample_bytes_per_epoch),
+        "precision0": extra.get("precision0"), "reddit": extra.get("reddit"),
+        "roofline": roof, "rooflines": rooflines, "spmm": spmm, "spmm_sharded": spmm_sharded, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         # device time of each phase of the epoch as a fraction of the timed region (CUDA events on the launch stream),
         # and the host time the main thread spent waiting for the sampler worker
         "phases": {k[6:]: round(v[1] / ms, 4) for k, v in sorted(kernel_times.items()) if k.startswith("phase_")},
@@ -415,6 +562,9 @@ def main():
     ap.add_argument("--workload", default="ogbn-arxiv", choices=list(WORKLOADS))
     ap.add_argument("--precision", type=int, default=int(os.environ.get("GS_GEMM_PRECISION", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary lines (precision 0, Reddit shape)")
+    ap.add_argument("--port", action="store_true", help="reference arm: time the oracle restatement even when the "
+                    "unmodified reference is staged under oracle/_ref")
     ns = ap.parse_args()
     if ns.impl == "reference":
         run_reference(ns)

@@ -34,19 +34,24 @@ def normalized_csr(K, adj):
     col = torch.from_numpy(a.indices.astype(np.int32)).to(dev)
     raw = torch.from_numpy(a.data.astype(np.float32)).to(dev)
     val = K.csr_gcn_norm(rowptr, col, raw, torch.from_numpy(r).to(dev))
-    at = a.T.tocsr()
-    at.sort_indices()
-    if not (np.array_equal(at.indptr, a.indptr) and np.array_equal(at.indices, a.indices)):
-        # the reference multiplies with SparseTensor(...).t(): the transpose of the normalised matrix
-        m = sp.csr_matrix((val.cpu().numpy(), a.indices, a.indptr), shape=a.shape).T.tocsr()
-        m.sort_indices()
-        rowptr = torch.from_numpy(m.indptr.astype(np.int32)).to(dev)
-        col = torch.from_numpy(m.indices.astype(np.int32)).to(dev)
-        val = torch.from_numpy(m.data.astype(np.float32)).to(dev)
+    val_host = val.cpu().numpy()
+    indptr, indices = a.indptr, a.indices
+    nt = sp.csr_matrix((val_host, a.indices, a.indptr), shape=a.shape).T.tocsr()
+    nt.sort_indices()
+    # the reference multiplies with SparseTensor(...).t(): the transpose of the NORMALISED matrix.  It equals the matrix
+    # itself only when structure AND values are symmetric (a directed or weighted graph is not)
+    if not (np.array_equal(nt.indptr, indptr) and np.array_equal(nt.indices, indices)
+            and np.array_equal(nt.data, val_host)):
+        indptr, indices = nt.indptr, nt.indices
+        rowptr = torch.from_numpy(indptr.astype(np.int32)).to(dev)
+        col = torch.from_numpy(indices.astype(np.int32)).to(dev)
+        val = torch.from_numpy(nt.data.astype(np.float32)).to(dev)
     chunks = None
     if dev.type == "cuda":
+        # long-row work items are built from the row pointer of the CSR that is actually returned (the transpose of a
+        # directed graph has different row lengths than the graph)
         from .graph_utils import build_row_chunks, chunks_to_device
-        chunks = chunks_to_device(build_row_chunks(a.indptr), dev)
+        chunks = chunks_to_device(build_row_chunks(indptr), dev)
     return Csr(rowptr, col, val, a.shape[0], a.shape[1], chunks)
 
 

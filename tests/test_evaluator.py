@@ -101,3 +101,51 @@ def test_reduce_with_checkpoints_runs_the_builtin_evaluator(tmp_path, monkeypatc
     saved = [f for _, _, fs in os.walk(tmp_path) for f in fs if f.endswith(".pt")]
     assert any(f.startswith("adj_") for f in saved) and any(f.startswith("feat_") for f in saved) and \
         any(f.startswith("label_") for f in saved)
+
+
+def _directed_hub_graph(n=400, hub_out=150, seed=0):
+    """A directed graph with one hub ROW (out-degree > the 64-nnz long-row threshold) whose transpose has a hub COLUMN
+    instead: the row lengths of the normalised matrix and of its transpose differ."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    rows = np.concatenate([np.zeros(hub_out, dtype=np.int64), rng.integers(1, n, 600)])
+    cols = np.concatenate([rng.choice(np.arange(1, n), hub_out, replace=False), rng.integers(0, n, 600)])
+    return sp.coo_matrix((np.ones(rows.size, dtype=np.float32), (rows, cols)), shape=(n, n)).tocsr()
+
+
+def test_normalized_csr_of_directed_graph_is_the_transpose():
+    """the returned CSR is the transpose of the normalised matrix (SparseTensor(...).t()), also when only
+    the VALUES are asymmetric; checked against scipy on the CPU-emulated kernels."""
+    import scipy.sparse as sp
+    from graphslim_b200.evaluation import normalized_csr
+    from tests.emu_ops import EmuOps
+    a = _directed_hub_graph()
+    K = EmuOps("cpu")
+    csr = normalized_csr(K, a)
+    b = (sp.csr_matrix(a, dtype=np.float64) + sp.eye(a.shape[0])).tocsr()
+    r = np.power(np.asarray(b.sum(1)).ravel(), -0.5)
+    ref = (sp.diags(r) @ b @ sp.diags(r)).T.tocsr()
+    ref.sort_indices()
+    assert np.array_equal(csr.rowptr.numpy(), ref.indptr) and np.array_equal(csr.col.numpy(), ref.indices)
+    np.testing.assert_allclose(csr.val.numpy(), ref.data.astype(np.float32), rtol=1e-6)
+    X = torch.randn(a.shape[0], 8)
+    np.testing.assert_allclose(K.spmm(csr, X).numpy(), (ref @ X.numpy().astype(np.float64)), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_normalized_csr_directed_hub_rows_on_cuda():
+    """The long-row chunk table must describe the returned (transposed) CSR: a hub column of the graph becomes a hub row
+    of the transpose, which the SpMM only covers through its chunk items."""
+    import scipy.sparse as sp
+    from graphslim_b200.evaluation import normalized_csr
+    from graphslim_b200.ops import CudaOps
+    a = _directed_hub_graph().T.tocsr()           # hub column -> the returned transpose has the hub ROW
+    K = CudaOps("cuda", precision=0)
+    csr = normalized_csr(K, a)
+    b = (sp.csr_matrix(a, dtype=np.float64) + sp.eye(a.shape[0])).tocsr()
+    r = np.power(np.asarray(b.sum(1)).ravel(), -0.5)
+    ref = (sp.diags(r) @ b @ sp.diags(r)).T.tocsr()
+    assert int(np.diff(ref.indptr).max()) > 64 and csr.chunks is not None
+    X = torch.randn(a.shape[0], 32)
+    got = K.spmm(csr, X.cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, ref @ X.numpy().astype(np.float64), rtol=1e-4, atol=1e-5)

@@ -51,6 +51,13 @@ def _mat(t, name):
 
 METRIC_ID = {"ours": 0, "mse": 1, "cos": 2}
 
+# gs_spmm_set_tuning is process-global library state: the record of what is currently set lives next to the library
+# handle (module level, lock-guarded), not per CudaOps instance -- one instance is created per reducer and the tests /
+# bench create more, so a per-instance cache could disagree with the library about the active tuning.
+import threading
+_SPMM_TUNE_LOCK = threading.Lock()
+_SPMM_TUNE = {"state": (0, 0)}
+
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 if _raw_stream is None:                      # older torch: the public (slower) route
@@ -229,28 +236,31 @@ class CudaOps:
         ldy = _mat(out, "out")
         # dense graph + wide rows: 64-float4 column tiles with 8 gathers in flight (1.2x at 492 nnz/row, F = 602; see
         # profiles/r1_spmm_sweep_v3.json).  The library cannot see nnz without a device read, the wrapper can.
-        tune = getattr(self, "_spmm_tune", (0, 0))
-        if tune != "manual":
-            want = (8, 2) if (F > 256 and csr.col.numel() >= 48 * csr.n_rows) else (0, 0)
-            if want != tune:
-                _lib.check(self.lib.gs_spmm_set_tuning(1, want[0], 0, 0, 0, want[1]), "gs_spmm_set_tuning")
-                self._spmm_tune = want
-        _lib.check(self.lib.gs_spmm_csr_f32(csr.n_rows, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val), _ptr(X), ldx,
-                                            F, _ptr(out), ldy, int(accumulate), n_chunks, int(thr), _ptr(cr),
-                                            _ptr(cb), _ptr(ce), self.stream), "gs_spmm_csr_f32")
+        with _SPMM_TUNE_LOCK:
+            tune = _SPMM_TUNE["state"]
+            if tune != "manual":
+                want = (8, 2) if (F > 256 and csr.col.numel() >= 48 * csr.n_rows) else (0, 0)
+                if want != tune:
+                    _lib.check(self.lib.gs_spmm_set_tuning(1, want[0], 0, 0, 0, want[1]), "gs_spmm_set_tuning")
+                    _SPMM_TUNE["state"] = want
+            _lib.check(self.lib.gs_spmm_csr_f32(csr.n_rows, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val), _ptr(X),
+                                                ldx, F, _ptr(out), ldy, int(accumulate), n_chunks, int(thr), _ptr(cr),
+                                                _ptr(cb), _ptr(ce), self.stream), "gs_spmm_csr_f32")
         return out
 
     def spmm_set_tuning(self, impl=1, unr=0, group=0, flags=0, wpb=0, max_nv=0):
         """Kernel generation / gathers in flight / rows per warp (v2) / cache hints / warps per CTA and widest column
         tile (v1) of the wide SpMM (include/graphslim_b200.h); 0 = the library's automatic choice.  An explicit call
         switches off the density heuristic of `spmm` until `spmm_auto_tuning()`."""
-        _lib.check(self.lib.gs_spmm_set_tuning(int(impl), int(unr), int(group), int(flags), int(wpb), int(max_nv)),
-                   "gs_spmm_set_tuning")
-        self._spmm_tune = "manual"
+        with _SPMM_TUNE_LOCK:
+            _lib.check(self.lib.gs_spmm_set_tuning(int(impl), int(unr), int(group), int(flags), int(wpb), int(max_nv)),
+                       "gs_spmm_set_tuning")
+            _SPMM_TUNE["state"] = "manual"
 
     def spmm_auto_tuning(self):
         self.spmm_set_tuning()
-        self._spmm_tune = (0, 0)
+        with _SPMM_TUNE_LOCK:
+            _SPMM_TUNE["state"] = (0, 0)
 
     def spmm_scatter(self, csr, dY, out):
         """out[col[e],:] += val[e]*dY[row(e),:] (atomics); `out` must be pre-initialised."""

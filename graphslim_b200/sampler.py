@@ -328,6 +328,11 @@ class _Prefetcher:
         self.t1.join(timeout=60)
         self.t2.join(timeout=60)
         self.stop = True
+        if self.t1.is_alive() or self.t2.is_alive():
+            # a worker that is still running holds (and rewrites) numpy's / torch's global generator state: carrying on
+            # would silently break the bit-exact stream contract
+            raise RuntimeError("sampler prefetch worker did not finish within 60 s; the random streams are in an "
+                               "undefined position")
 
 
 # =================================================================================================================
@@ -548,6 +553,10 @@ class _DevicePrefetcher:
             self.stop = True                     # consumer failed mid-epoch: streams stay where they are
         self.t.join(timeout=60)
         self.stop = True
+        if self.t.is_alive():
+            # the draw thread still owns the generators: checking the device stream back in over it would race
+            raise RuntimeError("device sampler draw thread did not finish within 60 s; the random streams are in an "
+                               "undefined position")
         if self.prev_slot is not None:
             self.s.release(self.prev_slot)
             self.prev_slot = None

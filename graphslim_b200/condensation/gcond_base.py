@@ -221,11 +221,23 @@ class GCondBase:
         return np.array(labels_syn)
 
     # ------------------------------------------------------------------ gcond_base.py:117-151 (init='random')
-    def init(self, with_adj=False):
-        """Random.select (sparsification/random.py:9-17) + MFCoreSet.reduce (model_free_coreset_base.py:16-61)."""
+    def init(self, with_adj=False, reuse_init=False):
+        """GCondBase.init (gcond_base.py:117-151): Random.select (sparsification/random.py:9-17) + MFCoreSet.reduce
+        (model_free_coreset_base.py:16-61), including the `--agg` variant whose initial features are the two-hop
+        aggregation A_hat^2 X of the selected nodes (full-graph SpMM, :18-27) and `reuse_init` (:134-143)."""
         args, data = self.args, self.data
         if args.init != "random":
-            raise NotImplementedError("init reducers other than 'random' are outside the GCond hot path")
+            raise NotImplementedError("init reducers other than 'random' (KCenter / Herding train a GCN on the full "
+                                      "graph first) are outside the GCond hot path")
+        if reuse_init:
+            base = f"{args.save_path}/reduced_graph/{args.init}"
+            tag = f"{args.dataset}_{args.reduction_rate}_{args.seed}.pt"
+            if os.path.exists(f"{base}/feat_{tag}") and (not with_adj or os.path.exists(f"{base}/adj_{tag}")):
+                feat = torch.load(f"{base}/feat_{tag}", map_location="cpu")
+                if not with_adj:
+                    return feat
+                adj = torch.load(f"{base}/adj_{tag}", map_location="cpu")
+                return feat, adj
         lt = np.asarray(data.labels_train)
         base = np.arange(len(data.idx_train)) if args.setting == "ind" else np.asarray(data.idx_train)
         picks = [np.random.permutation(base[lt == c])[:cnt] for c, cnt in self.num_class_dict.items()]
@@ -234,8 +246,25 @@ class GCondBase:
         src_feat = data.feat_full if args.setting == "trans" else data.feat_train
         src_adj = data.adj_full if args.setting == "trans" else data.adj_train
         src_lab = data.labels_full if args.setting == "trans" else data.labels_train
-        data.adj_syn = torch.from_numpy(np.asarray(src_adj[np.ix_(idx, idx)].todense())).float()
-        data.feat_syn = torch.as_tensor(src_feat)[torch.from_numpy(idx)].float()
+        if getattr(args, "agg", False):
+            if args.setting != "trans":
+                raise NotImplementedError("--agg init in the inductive setting: the reference multiplies a train-sized "
+                                          "operator with feat_full (model_free_coreset_base.py:37-41) and fails")
+            K = self.K
+            if getattr(self, "adj_csr", None) is None:
+                self._prepare_real()
+            csr = self._spmm_csr()
+            agg = K.spmm(csr, K.spmm(csr, self.features.contiguous()))        # A_hat (A_hat X) == (A_hat A_hat) X
+            data.feat_syn = agg[torch.from_numpy(idx).to(K.device)].float().cpu()
+            data.adj_syn = torch.eye(len(idx))
+        else:
+            # the reference keeps the induced adjacency as a coalesced sparse COO tensor (to_tensor of a scipy matrix,
+            # utils.py:240-247) -- also the format of the file it saves under reduced_graph/random
+            sub = src_adj[np.ix_(idx, idx)].tocoo()
+            data.adj_syn = torch.sparse_coo_tensor(torch.from_numpy(np.vstack([sub.row, sub.col]).astype(np.int64)),
+                                                   torch.from_numpy(sub.data.astype(np.float32)),
+                                                   torch.Size(sub.shape)).coalesce()
+            data.feat_syn = torch.as_tensor(src_feat)[torch.from_numpy(idx)].float()
         data.labels_syn = torch.as_tensor(src_lab)[torch.from_numpy(idx)].long()
         if getattr(args, "save_init", True):
             from ..dataset_utils import save_reduced
@@ -246,6 +275,17 @@ class GCondBase:
             finally:
                 args.method = keep
         return (data.feat_syn, data.adj_syn) if with_adj else data.feat_syn
+
+    def _spmm_csr(self):
+        """The full-graph normalised CSR with its long-row work items (power-law hubs), for the wide SpMM."""
+        if getattr(self, "_adj_csr_chunked", None) is None:
+            csr = self.adj_csr
+            if torch.device(self.K.device).type == "cuda":
+                from ..graph_utils import build_row_chunks, chunks_to_device
+                csr = Csr(csr.rowptr, csr.col, csr.val, csr.n_rows, csr.n_cols,
+                          chunks_to_device(build_row_chunks(self.adj_host[0]), self.K.device))
+            self._adj_csr_chunked = csr
+        return self._adj_csr_chunked
 
     # ------------------------------------------------------------------ real graph in HBM
     def _prepare_real(self):

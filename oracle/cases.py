@@ -67,6 +67,14 @@ CASES = {
         overrides=dict(outer_loop=3, hidden=32),
         keep_samples=1, keep_grads=2, grad_subsample=3,
     ),
+    # `--agg` init: initial features = two-hop aggregation A_hat^2 X of the selected nodes
+    # (sparsification/model_free_coreset_base.py:18-27), transductive SGC ntrans=1
+    "mini_sgc1_agg": dict(
+        dataset="cora", method="gcond", epochs=2,
+        graph=dict(n=600, und_edges=1500, d=96, c=5, split=(100, 100, 200), per_class_train=20, seed=3),
+        overrides=dict(outer_loop=3, inner_loop=2, agg=True),
+        keep_samples=1, keep_grads=2, grad_subsample=3,
+    ),
     # 'cos' metric on SGC ntrans=2
     "mini_sgc2_cos": dict(
         dataset="ogbn-arxiv", method="gcond", epochs=2, reduction_rate=0.05,

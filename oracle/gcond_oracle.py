@@ -369,6 +369,15 @@ class GCondOracle:
         ids = random_init_ids(data, self.alloc, args.setting)
         self.init_ids = ids
         src = data.feat_full if args.setting == "trans" else data.feat_train
+        if getattr(args, "agg", False):
+            # model_free_coreset_base.py:18-27: features aggregated over two hops, (A_hat A_hat) X with the sparse-sparse
+            # product first (trans only: the reference's 'ind' branch multiplies a train-sized operator with feat_full)
+            a = normalize_sparse(data.adj_full)
+            m = sp.csr_matrix((a.val, a.col, a.rowptr), shape=a.shape)
+            p2 = (m @ m).tocsr().astype(np.float32)
+            p2.sort_indices()
+            src = torch.from_numpy(hostlib.spmm_csr(p2.indptr.astype(np.int64), p2.indices.astype(np.int64), p2.data,
+                                                    data.feat_full.float().numpy()))
         self.feat_syn.data.copy_(src[torch.from_numpy(ids)].float())
         if self.x_variant:
             self.adj_syn = torch.eye(self.n_syn)

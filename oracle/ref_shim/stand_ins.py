@@ -149,9 +149,23 @@ class _SpMM(torch.autograd.Function):
         return _SpMM.apply(g.contiguous(), ctx.sp.t()), None
 
 
+def _spspmm(a, b):
+    """torch_sparse.matmul(SparseTensor, SparseTensor) (csrc spspmm: fp32 row-by-row accumulation): scipy's CSR
+    product in float32, columns sorted -- used by the `--agg` init only (model_free_coreset_base.py:20-24)."""
+    import scipy.sparse as sp
+    ma = sp.csr_matrix((a._value.numpy(), a._col.numpy(), a._rowptr.numpy()), shape=tuple(a._sizes))
+    mb = sp.csr_matrix((b._value.numpy(), b._col.numpy(), b._rowptr.numpy()), shape=tuple(b._sizes))
+    m = (ma @ mb).tocsr().astype(np.float32)
+    m.sort_indices()
+    return SparseTensor(rowptr=torch.from_numpy(m.indptr.astype(np.int64)), col=torch.from_numpy(m.indices.astype(np.int64)),
+                        value=torch.from_numpy(m.data), sparse_sizes=m.shape, is_sorted=True)
+
+
 def matmul(src, other, reduce="sum"):
     assert reduce == "sum"
-    assert isinstance(src, SparseTensor) and isinstance(other, torch.Tensor), "stand-in covers sparse @ dense only"
+    if isinstance(src, SparseTensor) and isinstance(other, SparseTensor):
+        return _spspmm(src, other)
+    assert isinstance(src, SparseTensor) and isinstance(other, torch.Tensor), "stand-in covers sparse @ dense / sparse"
     assert other.dim() == 2 and other.dtype == torch.float32
     return _SpMM.apply(other.contiguous(), src)
 

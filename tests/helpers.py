@@ -61,6 +61,7 @@ PARITY_TOL = {
     "mini_doscond_gcn": {0: (2e-3, 6e-3, 2e-2), 1: (2.5e-3, 6e-3, 2.5e-2)},
     "mini_doscondx_sgc2": {0: (1e-5, 1e-4, 1e-5), 1: (1e-5, 2e-3, 1e-5)},
     "mini_sgc2_cos": {0: (1e-5, 1e-4, 1e-5), 1: (1e-5, 2e-3, 1e-5)},
+    "mini_sgc1_agg": {0: (1e-4, 1e-4, 1e-4), 1: (2e-3, 2e-3, 1e-3)},
 }
 
 

@@ -131,7 +131,12 @@ def check_against_golden(gold, sub, args, data, agent, seen, pge_init, first_tol
     got_init = np.stack(seen["model_init"])
     assert np.array_equal(got_init, gold["model_init"][:len(got_init)])
     # Random init (gcond_base.py:117-151 -> sparsification/random.py): the selected rows, bit exact
-    assert np.array_equal(seen["feat_init"][:, ::sub], gold["feat_init"])
+    if getattr(args, "agg", False):
+        # aggregated init: A_hat (A_hat X) here vs (A_hat A_hat) X in the reference -- same rows, fp32 reassociation
+        np.testing.assert_allclose(seen["feat_init"][:, ::sub], gold["feat_init"], rtol=1e-4,
+                                   atol=1e-5 * np.abs(gold["feat_init"]).max())
+    else:
+        assert np.array_equal(seen["feat_init"][:, ::sub], gold["feat_init"])
     if "adj_syn0" in seen and "adj_syn_norm0" in gold.files:
         # first normalised synthetic adjacency dense_gcn_norm(pge(feat_syn)) (gcond.py:48-49)
         a0, r0 = seen["adj_syn0"], gold["adj_syn_norm0"]

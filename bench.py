@@ -230,7 +230,7 @@ def run_reference(ns):
 
 
 # --------------------------------------------------------------------------------------- our arm
-def spmm_probe(agent, pk, iters=10):
+def spmm_probe(agent, pk, iters=10, tile_cols=None):
     """Standalone full-graph A_hat @ X on the workload's graph (BASELINE config 5 at this shape)."""
     import torch
     from graphslim_b200.graph_utils import build_row_chunks, chunks_to_device
@@ -250,7 +250,7 @@ def spmm_probe(agent, pk, iters=10):
         flush.zero_()                                   # evict L2 (126 MB) between iterations
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        K.spmm(csr, X, out=out)
+        K.spmm(csr, X, out=out, tile_cols=tile_cols)
         b.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -258,8 +258,16 @@ def spmm_probe(agent, pk, iters=10):
     ms = statistics.median(ts)
     alg = 4 * (n + 1) + 8 * nnz + 4 * F * n + 4 * F * n
     gather = 4 * (n + 1) + 8 * nnz + 4 * F * nnz + 4 * F * n
-    return {"kernel": "gs_spmm_csr_f32 full graph", "n": n, "nnz": nnz, "F": F, "ms": ms,
-            "alg_GBps": alg / ms / 1e6, "alg_frac_of_hbm": alg / ms / 1e6 / pk["hbm"],
+    tile = K.spmm_tile_cols(csr, X) if tile_cols is None else tile_cols
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    tr = (json.load(open(tpath)).get("spmm", {}) if os.path.exists(tpath) else {}).get(f"n{n}_F{F}") or {}
+    # roofline of the SpMM: algorithmic (compulsory) bytes against the measured copy peak; the gather
+    # model and the ncu DRAM traffic of one launch (when captured) beside it
+    return {"kernel": "gs_spmm_csr_f32 full graph" + (f", L2-resident column slices of {tile} floats" if tile else ""),
+            "bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": alg / ms / 1e6 / pk["hbm"], "traffic": tr.get("dram_bytes_per_launch"),
+            "traffic_source": tr.get("source"), "n": n, "nnz": nnz, "F": F, "ms": ms, "tile_cols": tile,
+            "alg_bytes_per_launch": alg, "alg_GBps": alg / ms / 1e6, "alg_frac_of_hbm": alg / ms / 1e6 / pk["hbm"],
             "gather_GBps": gather / ms / 1e6, "l2_flushed": True}
 
 
@@ -336,10 +344,16 @@ def quick_epochs(workload, precision, steps, warmup, world, rank, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     n_syn = int(agent.nnodes_syn)
+    spmm = None
+    if workload == "reddit" and rank == 0:
+        # the full-graph A_hat X of this shape: X (n x 602 fp32) is several times the L2, so the wide kernel sweeps it in
+        # L2-resident column slices (gs_spmm_csr_tiled_f32); the untiled time is kept beside it
+        spmm = spmm_probe(agent, peaks(), iters=5)
+        spmm["untiled_ms"] = spmm_probe(agent, peaks(), iters=3, tile_cols=0)["ms"]
     del agent, data, raw
     torch.cuda.empty_cache()
     return {"workload": WORKLOADS[workload], "gemm_precision": precision, "value": steps / (ms / 1e3), "unit": "epochs/s",
-            "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "n_gpus": world, "n_syn": n_syn}
+            "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "n_gpus": world, "n_syn": n_syn, "spmm": spmm}
 
 
 def run_ours(ns):

@@ -20,6 +20,8 @@ SIGNATURES = {
     "gs_last_error": (ctypes.c_char_p, []),
     "gs_spmm_csr_f32": (c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_int, c_i32, c_i32, c_vp,
                                 c_vp, c_vp, c_vp]),
+    "gs_spmm_csr_tiled_f32": (c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_int, c_i32, c_i32, c_vp,
+                                      c_vp, c_vp, c_i32, c_vp]),
     "gs_spmm_set_tuning": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "gs_spmm_csr_scatter_f32": (c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "gs_gather_rows_f32": (c_int, [c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),

@@ -4,6 +4,7 @@ PyTorch only supplies device memory and the stream here.  Every method launches 
 kernels from libgraphslim_b200.so on the current CUDA stream; CPU tensors are rejected.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -224,7 +225,7 @@ class CudaOps:
         return self.segment_colsum(X, seg, ob, 1)
 
     # -- sparse --------------------------------------------------------------------------------
-    def spmm(self, csr, X, out=None, accumulate=False):
+    def spmm(self, csr, X, out=None, accumulate=False, tile_cols=None):
         ldx = _mat(X, "X")
         F = X.shape[1]
         n_chunks, thr, cr, cb, ce = 0, 0, None, None, None
@@ -236,6 +237,14 @@ class CudaOps:
         ldy = _mat(out, "out")
         # dense graph + wide rows: 64-float4 column tiles with 8 gathers in flight (1.2x at 492 nnz/row, F = 602; see
         # profiles/r1_spmm_sweep_v3.json).  The library cannot see nnz without a device read, the wrapper can.
+        tile = self.spmm_tile_cols(csr, X) if tile_cols is None else int(tile_cols)
+        if tile and tile < F:
+            # X does not fit the L2: sweep it in L2-resident column slices (gs_spmm_csr_tiled_f32)
+            _lib.check(self.lib.gs_spmm_csr_tiled_f32(csr.n_rows, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val),
+                                                      _ptr(X), ldx, F, _ptr(out), ldy, int(accumulate), n_chunks,
+                                                      int(thr), _ptr(cr), _ptr(cb), _ptr(ce), tile, self.stream),
+                       "gs_spmm_csr_tiled_f32")
+            return out
         with _SPMM_TUNE_LOCK:
             tune = _SPMM_TUNE["state"]
             if tune != "manual":
@@ -247,6 +256,22 @@ class CudaOps:
                                                 ldx, F, _ptr(out), ldy, int(accumulate), n_chunks, int(thr), _ptr(cr),
                                                 _ptr(cb), _ptr(ce), self.stream), "gs_spmm_csr_f32")
         return out
+
+    # bytes of a gathered column slice that may live in the 126 MB L2 next to the streamed (col, val) / Y traffic
+    SPMM_L2_BUDGET = int(os.environ.get("GS_SPMM_L2_BUDGET", 64 << 20))
+
+    def spmm_tile_cols(self, csr, X):
+        """Width (floats, multiple of 32) of the L2-resident column slices the wide SpMM should sweep, or 0 for the
+        untiled kernel: tiling pays when X exceeds the L2, a >= 128-byte slice of every source row still fits, and the
+        graph is dense enough that re-gathered feature rows (4 F B / nnz) outweigh the re-read indices (8 B / nnz / slice)."""
+        F = X.shape[1]
+        n_src = max(int(csr.n_cols), 1)
+        if X.stride(0) % 4 or X.data_ptr() % 16 or F < 64 or n_src * F * 4 <= 2 * self.SPMM_L2_BUDGET:
+            return 0
+        tile = (self.SPMM_L2_BUDGET // (n_src * 4)) // 32 * 32
+        if tile < 32 or tile >= F or csr.col.numel() < 16 * csr.n_rows:
+            return 0
+        return int(tile)
 
     def spmm_set_tuning(self, impl=1, unr=0, group=0, flags=0, wpb=0, max_nv=0):
         """Kernel generation / gathers in flight / rows per warp (v2) / cache hints / warps per CTA and widest column

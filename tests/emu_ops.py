@@ -78,7 +78,7 @@ class EmuOps:
         rows = torch.repeat_interleave(torch.arange(csr.n_rows, device=csr.rowptr.device), counts)
         return rows, csr.col.long()
 
-    def spmm(self, csr, X, out=None, accumulate=False):
+    def spmm(self, csr, X, out=None, accumulate=False, tile_cols=None):
         rows, cols = self._coo(csr)
         y = torch.zeros(csr.n_rows, X.shape[1], device=self.device)
         y.index_add_(0, rows, csr.val[:, None] * X[cols])

@@ -176,6 +176,32 @@ def test_spmm_transpose_and_scatter_agree(K, E):
     close(got, ref)
 
 
+def test_spmm_l2_column_tiling_bit_identical(K):
+    """gs_spmm_csr_tiled_f32 (X swept in L2-resident column slices) produces the bits of the untiled kernel, with and
+    without long-row work items, for slice widths that do and do not divide F."""
+    from graphslim_b200.graph_utils import build_row_chunks, chunks_to_device
+    from graphslim_b200.ops import Csr
+    gen = torch.Generator().manual_seed(5)
+    n, F = 3000, 602
+    deg = torch.randint(1, 40, (n,), generator=gen)
+    deg[7] = 900                                            # a hub row
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.int64), deg.cumsum(0)]).to(torch.int32)
+    nnz = int(rowptr[-1])
+    col = torch.randint(0, n, (nnz,), generator=gen).to(torch.int32)
+    val = torch.rand(nnz, generator=gen)
+    Xp = torch.zeros(n, 608)
+    Xp[:, :F] = torch.randn(n, F, generator=gen)
+    X = Xp.cuda()[:, :F]
+    chunks = chunks_to_device(build_row_chunks(rowptr.numpy(), 64), "cuda")
+    for ch in (None, chunks):
+        csr = Csr(rowptr.cuda(), col.cuda(), val.cuda(), n, n, ch)
+        ref = K.spmm(csr, X, tile_cols=0)
+        for tile in (32, 64, 96, 256):
+            assert torch.equal(K.spmm(csr, X, tile_cols=tile), ref)
+    # the automatic choice: nothing to tile for a matrix that fits the L2
+    assert K.spmm_tile_cols(csr, X) == 0
+
+
 def test_gather_rows(K):
     gen = np.random.default_rng(1)
     X = torch.from_numpy(gen.standard_normal((1000, 602)).astype(np.float32)).cuda()

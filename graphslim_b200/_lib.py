@@ -33,6 +33,11 @@ SIGNATURES = {
                                 c_vp, c_int, c_vp, c_i64, c_int, c_vp, c_i64, c_vp]),
     "gs_gemm_grouped_tn_f32": (c_int, [c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
                                        c_int, c_vp, c_i64, c_vp]),
+    "gs_gemm_grouped_mn_supported": (c_int, [c_i32, c_i32, c_int]),
+    "gs_gemm_grouped_mn_f32": (c_int, [c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
+                                       c_int, c_vp]),
+    "gs_mlp_bwd_grouped_f32": (c_int, [c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp,
+                                       c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_vp]),
     "gs_segment_colsum_f32": (c_int, [c_i32, c_vp, c_vp, c_i32, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "gs_bias_act_f32": (c_int, [c_i32, c_i32, c_vp, c_i64, c_vp, c_int, c_vp]),
     "gs_relu_mask_f32": (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),

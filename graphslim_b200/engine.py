@@ -178,9 +178,13 @@ class SGC2(_ModelBase):
         seg, ids, nb = rb.seg[-1], rb.out_block, self.lay.nblk
         gW2 = K.gemm_grouped_tn(H1, dU, seg, ids, nb, aligned=rb.aligned)
         gb2 = K.segment_colsum(dU, seg, ids, nb)
-        dA1 = K.gemm(dU, W2, tb=True, mask=H1)
-        gW1 = K.gemm_grouped_tn(Xg, dA1, seg, ids, nb, aligned=rb.aligned)
-        gb1 = K.segment_colsum(dA1, seg, ids, nb)
+        if K.mlp_bwd_grouped_supported(Xg, H1, dU, rb.aligned):
+            # dA1 = (dU W2^T) . [H1 > 0] generated inside the grouped product: never written to / re-read from HBM
+            gW1, gb1 = K.mlp_bwd_grouped(Xg, H1, dU, W2, seg, ids, nb)
+        else:
+            dA1 = K.gemm(dU, W2, tb=True, mask=H1)
+            gW1 = K.gemm_grouped_tn(Xg, dA1, seg, ids, nb, aligned=rb.aligned)
+            gb1 = K.segment_colsum(dA1, seg, ids, nb)
         return [gW1, gb1, gW2, gb2]
 
     def syn_forward(self, X, A):
@@ -287,9 +291,12 @@ class GCN2(_ModelBase):
         dM2 = K.spmm(inner.csr_t, R)
         seg1 = rb.seg[1]
         gW2 = K.gemm_grouped_tn(H1, dM2, seg1, ids, nb, aligned=rb.aligned)
-        dA1 = K.gemm(dM2, W2, tb=True, mask=H1)
-        gb1 = K.segment_colsum(dA1, seg1, ids, nb)
-        gW1 = K.gemm_grouped_tn(T2, dA1, seg1, ids, nb, aligned=rb.aligned)
+        if K.mlp_bwd_grouped_supported(T2, H1, dM2, rb.aligned):
+            gW1, gb1 = K.mlp_bwd_grouped(T2, H1, dM2, W2, seg1, ids, nb)
+        else:
+            dA1 = K.gemm(dM2, W2, tb=True, mask=H1)
+            gb1 = K.segment_colsum(dA1, seg1, ids, nb)
+            gW1 = K.gemm_grouped_tn(T2, dA1, seg1, ids, nb, aligned=rb.aligned)
         return [gW1, gb1, gW2, gb2]
 
     def syn_forward(self, X, A):

@@ -191,6 +191,13 @@ class CudaOps:
         M, N, Kt = A.shape[1], B.shape[1], A.shape[0]
         G = seg.numel() - 1
         prec = (self.precision if precision is None else precision) if aligned else 0
+        if prec and self._mn_ok(A, lda, B, ldb, M, N, prec):
+            # both operands consumed row-major through TMA as MN-major UMMA operands (csrc/grouped_tn.cu)
+            out = self.zeros(M, nblk * N)
+            _lib.check(self.lib.gs_gemm_grouped_mn_f32(G, _ptr(seg), _ptr(out_block), M, N, Kt, _ptr(A), lda, _ptr(B),
+                                                       ldb, _ptr(out), nblk * N, prec, self.stream),
+                       "gs_gemm_grouped_mn_f32")
+            return out
         ws, ws_bytes = None, 0
         if prec:
             ws_bytes = int(self.lib.gs_gemm_workspace_bytes(M, N, Kt, prec))
@@ -201,6 +208,29 @@ class CudaOps:
                                                    _ptr(out), nblk * N, prec, _ptr(ws), ws_bytes, self.stream),
                    "gs_gemm_grouped_tn_f32")
         return out
+
+    def _mn_ok(self, A, lda, B, ldb, M, N, prec):
+        return (getattr(self, "grouped_mn", True) and lda % 4 == 0 and ldb % 4 == 0 and A.data_ptr() % 16 == 0
+                and B.data_ptr() % 16 == 0 and (N * 4) % 16 == 0
+                and bool(self.lib.gs_gemm_grouped_mn_supported(M, N, prec)))
+
+    def mlp_bwd_grouped_supported(self, X, H1, dU, aligned):
+        prec = self.precision
+        return (aligned and prec in (1, 2) and getattr(self, "grouped_mn", True) and X.shape[1] in (128, 256)
+                and H1.shape[1] == 256 and dU.shape[1] % 4 == 0 and 4 <= dU.shape[1] <= 64
+                and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (X, H1, dU)))
+
+    def mlp_bwd_grouped(self, X, H1, dU, W2, seg, out_block, nblk):
+        """(gW1, gb1) of the hidden layer on the real side for all classes: dA1 = (dU W2^T) . [H1 > 0] is generated on
+        chip, gW1 block g = X[rows g]^T dA1[rows g], gb1 block g = column sums of dA1[rows g]  (csrc/grouped_tn.cu)."""
+        ldx, ldh, ldu, ldw = _mat(X, "X"), _mat(H1, "H1"), _mat(dU, "dU"), _mat(W2, "W2")
+        M, N, Cw, Kt = X.shape[1], H1.shape[1], dU.shape[1], X.shape[0]
+        G = seg.numel() - 1
+        gW1, gb1 = self.zeros(M, nblk * N), self.zeros(1, nblk * N)
+        _lib.check(self.lib.gs_mlp_bwd_grouped_f32(G, _ptr(seg), _ptr(out_block), M, N, Cw, Kt, _ptr(X), ldx, _ptr(H1),
+                                                   ldh, _ptr(dU), ldu, _ptr(W2), ldw, _ptr(gW1), nblk * N, _ptr(gb1),
+                                                   self.precision, self.stream), "gs_mlp_bwd_grouped_f32")
+        return gW1, gb1
 
     def segment_colsum(self, X, seg, out_block, nblk):
         """(1 x nblk*cols): block out_block[g] holds the column sums of rows seg[g]..seg[g+1] of X; other blocks zero."""

@@ -54,7 +54,7 @@ int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, c
 
 /* The same product run `tile_cols` feature columns at a time (a multiple of 4; the caller sizes n_src * tile_cols * 4 B
  * to fit the L2), for X larger than the L2: the gathered column slice stays L2-resident while the rows sweep it, at the
- * price of re-reading (col, val) once per slice.  Bit-identical to gs_spmm_csr_f32. */
+ * price of re-reading (col, val) once per slice.  Bit-identical to gs_spmm_csr_f32 for tile_cols >= 128, equal up to fp32 reassociation below. */
 int gs_spmm_csr_tiled_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
                           int64_t ldx, int32_t F, float* Y, int64_t ldy, int accumulate, int32_t n_chunks,
                           int32_t long_thr, const int32_t* chunk_row, const int32_t* chunk_beg,
@@ -248,6 +248,25 @@ int gs_pge_bn1_bwd_pass_rows_f32(int32_t n_i, int32_t i_first, int32_t n, int32_
 int gs_pge_bn1_bwd_final_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, const float* rstd,
                              const float* gamma, const float* col_mean, const void* work, float* dPa, float* dPb,
                              float* dgamma, float* dbeta, void* stream);
+
+/* ---- grouped TN products with MN-major, TMA-fed operands (csrc/grouped_tn.cu): the per-class weight gradients of the
+ * real side, autograd.grad(loss_real, params) of condensation/gcond_base.py:221-224 for all classes at once.
+ *   gs_gemm_grouped_mn_supported  1 when the shape is covered (M in {128, 256}; N in {128, 256} or N <= 64 with N % 4 == 0;
+ *                                 precision 1 or 2), else use gs_gemm_grouped_tn_f32
+ *   gs_gemm_grouped_mn_f32        C[:, out_block[g]*N : +N] += A[seg[g]:seg[g+1]]^T B[seg[g]:seg[g+1]] (C zeroed by the
+ *                                 caller, segments 64-aligned); A, B row-major fp32 read by cp.async.bulk.tensor and
+ *                                 converted to BF16 hi/lo in place in shared memory, no packing or transposition in HBM
+ *   gs_mlp_bwd_grouped_f32        backward of the hidden ReLU layer of the 2-layer condense models (models/sgc.py:37-57,
+ *                                 layers.py:36-51 under autograd): dA1 = (dU W2^T) . [H1 > 0] generated per k-stage on
+ *                                 chip, gW1 += X^T dA1 and gb1 += colsum(dA1) per class; dA1 never reaches HBM */
+int gs_gemm_grouped_mn_supported(int32_t M, int32_t N, int precision);
+int gs_gemm_grouped_mn_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t M, int32_t N,
+                           int32_t total_rows, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                           int64_t ldc, int precision, void* stream);
+int gs_mlp_bwd_grouped_f32(int32_t G, const int32_t* seg, const int32_t* out_block, int32_t M, int32_t N, int32_t Cw,
+                           int32_t total_rows, const float* X, int64_t ldx, const float* H1, int64_t ldh,
+                           const float* dU, int64_t ldu, const float* W2, int64_t ldw2, float* gW1, int64_t ldc,
+                           float* gb1, int precision, void* stream);
 
 /* ---- fused PGE layer-2 pipeline (csrc/pge_fused.cu): tcgen05 + TMEM products whose N'^2 x h operands are produced on
  * chip, replacing gs_pge_l1_expand + gs_gemm + gs_col_stats (forward) and gs_pge_bn2_bwd_apply + two gs_gemm +

@@ -60,6 +60,13 @@ class EmuOps:
             out[:, ob * N:(ob + 1) * N] = A[r0:r1].T @ B[r0:r1]
         return out
 
+    def mlp_bwd_grouped_supported(self, X, H1, dU, aligned):
+        return bool(getattr(self, "fuse_mlp_bwd", True))
+
+    def mlp_bwd_grouped(self, X, H1, dU, W2, seg, out_block, nblk):
+        dA1 = (dU @ W2.T) * (H1 > 0)
+        return self.gemm_grouped_tn(X, dA1, seg, out_block, nblk), self.segment_colsum(dA1, seg, out_block, nblk)
+
     def segment_colsum(self, X, seg, out_block, nblk):
         cols = X.shape[1]
         out = torch.zeros(1, nblk * cols, device=self.device)

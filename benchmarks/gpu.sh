@@ -50,7 +50,7 @@ PY
       ( time timeout 900 python bench.py --impl reference --workload $a --steps 3 --warmup 1 ) > $log 2>&1; tail -3 $log | cut -c1-600 ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
-        --log-file gpurun_out/${TAG}_launches_${a}.csv python bench.py --workload $a --steps 1 --warmup 1 --no-cpu-baseline \
+        --log-file gpurun_out/${TAG}_launches_${a}.csv python bench.py --workload $a --steps 1 --warmup 1 --no-cpu-baseline --no-extra \
         > gpurun_out/${TAG}_bench_under_ncu_${a}.log 2>&1
       echo "launch list rc=$? ($(wc -l < gpurun_out/${TAG}_launches_${a}.csv) lines)" ;;
     pge)

@@ -454,54 +454,50 @@ pge_bn1_bwd_reduce_kernel(int n, int h, const float* __restrict__ dH1, const flo
 // Layer-1 pre-activations are Pa[j] + Pb[i] over the full product set {i} x {j}, so their batch statistics
 // factorise exactly:  mean = mean_j(Pa) + mean_i(Pb),  var = var_j(Pa) + var_i(Pb)  (the cross term sums to 0).
 // 2n rows are read instead of n^2.  col_mean[0][c] / [1][c] keep the column means of Pa / Pb for the backward.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 pge_l1_stats_closed_kernel(int n, int h, const float* __restrict__ Pa, const float* __restrict__ Pb, float eps,
                            float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ col_mean) {
-  __shared__ double sm[2][8][33];
-  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;          // 32 columns x 8 row groups
+  // 32 columns x 32 row groups per block, ONE pass: sums of (x - x_row0) and (x - x_row0)^2 in double (the shift keeps
+  // the second moment variance-sized), combined across the row groups through shared memory
+  __shared__ double sm[4][32][33];
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const bool live = c < h;
-  double sa = 0.0, sb = 0.0;
+  double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0, a0 = 0.0, b0 = 0.0;
   if (live) {
+    a0 = (double)__ldg(Pa + c);
+    b0 = (double)__ldg(Pb + c);
 #pragma unroll 4
-    for (int r = rg; r < n; r += 8) {
-      sa += (double)__ldg(Pa + (int64_t)r * h + c);
-      sb += (double)__ldg(Pb + (int64_t)r * h + c);
+    for (int r = rg; r < n; r += 32) {
+      const double da = (double)__ldg(Pa + (int64_t)r * h + c) - a0, db = (double)__ldg(Pb + (int64_t)r * h + c) - b0;
+      a1 += da;
+      a2 = fma(da, da, a2);
+      b1 += db;
+      b2 = fma(db, db, b2);
     }
   }
-  sm[0][rg][cl] = sa;
-  sm[1][rg][cl] = sb;
-  __syncthreads();
-  double ma = 0.0, mb = 0.0;
-#pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    ma += sm[0][g][cl];
-    mb += sm[1][g][cl];
-  }
-  ma /= (double)n;
-  mb /= (double)n;
-  __syncthreads();
-  double va = 0.0, vb = 0.0;
-  if (live) {
-#pragma unroll 4
-    for (int r = rg; r < n; r += 8) {
-      const double da = (double)__ldg(Pa + (int64_t)r * h + c) - ma, db = (double)__ldg(Pb + (int64_t)r * h + c) - mb;
-      va = fma(da, da, va);
-      vb = fma(db, db, vb);
-    }
-  }
-  sm[0][rg][cl] = va;
-  sm[1][rg][cl] = vb;
+  sm[0][rg][cl] = a1;
+  sm[1][rg][cl] = a2;
+  sm[2][rg][cl] = b1;
+  sm[3][rg][cl] = b2;
   __syncthreads();
   if (rg == 0 && live) {
-    double v = 0.0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) v += sm[0][g][cl] + sm[1][g][cl];
-    v /= (double)n;
-    mean[c] = (float)(ma + mb);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+    for (int g = 0; g < 32; ++g) {
+      s[0] += sm[0][g][cl];
+      s[1] += sm[1][g][cl];
+      s[2] += sm[2][g][cl];
+      s[3] += sm[3][g][cl];
+    }
+    const double inv = 1.0 / (double)n;
+    const double ma = s[0] * inv, mb = s[2] * inv;
+    double v = (s[1] * inv - ma * ma) + (s[3] * inv - mb * mb);
+    if (v < 0.0) v = 0.0;
+    mean[c] = (float)(a0 + ma + b0 + mb);
     rstd[c] = (float)(1.0 / sqrt(v + (double)eps));
-    col_mean[c] = (float)ma;
-    col_mean[h + c] = (float)mb;
+    col_mean[c] = (float)(a0 + ma);
+    col_mean[h + c] = (float)(b0 + mb);
   }
 }
 
@@ -554,6 +550,89 @@ pge_l3_fast_kernel(int64_t rows, const float* __restrict__ Y2, const float* __re
       const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
       E[r + lane] = v + bias;
     }
+  }
+}
+
+// Layer-3 + BN2 backward statistics for h = 128*NQ, unchunked: a warp streams whole rows (coalesced 512 B * NQ per row, four
+// rows in flight), every lane keeps the sums of its 4*NQ columns in registers (s1 = sum d, s2 = sum d*xhat, dw3 = sum
+// dE*relu(yhat) with d = dE*w3 where yhat > 0), per-column constants live in registers too.  The warps of a block are
+// combined through shared memory and leave one double atomic per column, statistic and block.  The generic slice kernel
+// (pge_l3_bwd_partial_kernel) ran at ~55 % of the copy bandwidth on this stream; this one is the mirror of pge_l3_fast.
+template <int NQ>
+__global__ void __launch_bounds__(256)
+pge_l3_bwd_fast_kernel(int64_t rows, const float* __restrict__ Y2, const float* __restrict__ dE,
+                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ w3, double* __restrict__ work) {
+  constexpr int h = 128 * NQ;
+  constexpr int U = 4;
+  __shared__ float sm[8][3][h];
+  __shared__ float sm_db[8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  float4 m[NQ], s[NQ], g[NQ], b[NQ], w[NQ], a1[NQ], a2[NQ], a3[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int k = lane * 4 + 128 * q;
+    m[q] = ld4(mean + k); s[q] = ld4(rstd + k); g[q] = ld4(gamma + k); b[q] = ld4(beta + k); w[q] = ld4(w3 + k);
+    a1[q] = a2[q] = a3[q] = f4_zero();
+  }
+  float db = 0.f;
+  // contiguous share of the rows per warp (keeps every warp's stream sequential)
+  const int64_t per = (rows + nwarps - 1) / nwarps;
+  const int64_t r_beg = warp * per, r_end = min(rows, r_beg + per);
+  for (int64_t r = r_beg; r < r_end; r += U) {
+    float4 y[U][NQ];
+    float de[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = (r + u < r_end) ? r + u : r_end - 1;
+      de[u] = (r + u < r_end) ? __ldg(dE + rr) : 0.f;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) y[u][q] = ld4(Y2 + rr * h + lane * 4 + 128 * q);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (lane == 0) db += de[u];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+#define GS_L3F(cmp)                                                   \
+  {                                                                   \
+    const float xh = (y[u][q].cmp - m[q].cmp) * s[q].cmp;             \
+    const float yh = fmaf(g[q].cmp, xh, b[q].cmp);                    \
+    if (yh > 0.f) {                                                   \
+      const float d = de[u] * w[q].cmp;                               \
+      a1[q].cmp += d;                                                 \
+      a2[q].cmp = fmaf(d, xh, a2[q].cmp);                             \
+      a3[q].cmp = fmaf(de[u], yh, a3[q].cmp);                         \
+    }                                                                 \
+  }
+        GS_L3F(x) GS_L3F(y) GS_L3F(z) GS_L3F(w)
+#undef GS_L3F
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int k = lane * 4 + 128 * q;
+    *reinterpret_cast<float4*>(&sm[wib][0][k]) = a1[q];
+    *reinterpret_cast<float4*>(&sm[wib][1][k]) = a2[q];
+    *reinterpret_cast<float4*>(&sm[wib][2][k]) = a3[q];
+  }
+  if (lane == 0) sm_db[wib] = db;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 3 * h; idx += 256) {
+    const int st = idx / h, k = idx % h;
+    float acc = 0.f;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc += sm[v][st][k];
+    atomicAdd(work + (int64_t)st * h + k, (double)acc);      // work = [s1 (h) | s2 (h) | dw3 (h) | db3]
+  }
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc += sm_db[v];
+    atomicAdd(work + 3 * h, (double)acc);
   }
 }
 
@@ -668,7 +747,7 @@ int gs_pge_l1_stats_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, 
 int gs_pge_l1_stats_closed_f32(int32_t n, int32_t h, const float* Pa, const float* Pb, float eps, float* mean,
                                float* rstd, float* col_mean, void* stream) {
   GS_REQUIRE(n > 0 && h > 0 && Pa && Pb && mean && rstd && col_mean);
-  pge_l1_stats_closed_kernel<<<(h + 31) / 32, 256, 0, as_stream(stream)>>>(n, h, Pa, Pb, eps, mean, rstd, col_mean);
+  pge_l1_stats_closed_kernel<<<(h + 31) / 32, 1024, 0, as_stream(stream)>>>(n, h, Pa, Pb, eps, mean, rstd, col_mean);
   return finish_launch("pge_l1_stats_closed");
 }
 
@@ -836,8 +915,18 @@ int gs_pge_l3_bwd_stats_f32(int64_t rows, int32_t h, const float* Y2, const floa
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(work, 0, sizeof(double) * (2 * nchunk * h + h + 1), st);
   Chunks ch{nchunk, chunk_off};
-  pge_l3_bwd_partial_kernel<<<slice_grid(rows, nchunk), 256, 0, st>>>(h, Y2, dE, ch, mean, rstd, gamma, beta, w3, work);
-  int rc = finish_launch("pge_l3_bwd_partial");
+  int rc;
+  if (nchunk == 1 && (h == 128 || h == 256) && (reinterpret_cast<uintptr_t>(Y2) & 15) == 0) {
+    // same work layout as the slice kernel for one chunk: [s1 | s2 | dw3 | db3]
+    const int64_t want = (rows + 63) / 64;
+    const unsigned grid = (unsigned)(want < kNumSMs * 8 ? want : kNumSMs * 8);
+    if (h == 128) pge_l3_bwd_fast_kernel<1><<<grid, 256, 0, st>>>(rows, Y2, dE, mean, rstd, gamma, beta, w3, work);
+    else pge_l3_bwd_fast_kernel<2><<<grid, 256, 0, st>>>(rows, Y2, dE, mean, rstd, gamma, beta, w3, work);
+    rc = finish_launch("pge_l3_bwd_fast");
+  } else {
+    pge_l3_bwd_partial_kernel<<<slice_grid(rows, nchunk), 256, 0, st>>>(h, Y2, dE, ch, mean, rstd, gamma, beta, w3, work);
+    rc = finish_launch("pge_l3_bwd_partial");
+  }
   if (rc) return rc;
   const int cnt = nchunk * h;
   pge_l3_bwd_final_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(h, nchunk, work, s1, s2, dw3, db3);

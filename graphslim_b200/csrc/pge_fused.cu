@@ -870,13 +870,16 @@ __global__ void __launch_bounds__(256)
 bn1_tsum_kernel(int n, int h, const float* __restrict__ Pa, const float* __restrict__ Pb,
                 const float* __restrict__ col_mean, const float* __restrict__ rstd, const float* __restrict__ Ga,
                 const float* __restrict__ Gb, double* __restrict__ tsum) {
+  // 32 columns x 8 row groups per block; blockIdx.y splits the rows (one double atomic per column, statistic and block)
   __shared__ double sm[2][8][33];
   const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
+  const int per = (n + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(n, r0 + per);
   double a1 = 0.0, a2 = 0.0;
   if (c < h) {
     const double ma = (double)col_mean[c], mb = (double)col_mean[h + c];
-    for (int r = rg; r < n; r += 8) {
+    for (int r = r0 + rg; r < r1; r += 8) {
       const double ga = (double)Ga[(int64_t)r * h + c], gb = (double)Gb[(int64_t)r * h + c];
       a1 += ga;
       a2 += ga * ((double)Pa[(int64_t)r * h + c] - ma) + gb * ((double)Pb[(int64_t)r * h + c] - mb);
@@ -892,8 +895,8 @@ bn1_tsum_kernel(int n, int h, const float* __restrict__ Pa, const float* __restr
       t1 += sm[0][g][cl];
       t2 += sm[1][g][cl];
     }
-    tsum[c] += t1;
-    tsum[h + c] += t2 * (double)rstd[c];
+    atomicAdd(tsum + c, t1);
+    atomicAdd(tsum + h + c, t2 * (double)rstd[c]);
   }
 }
 
@@ -1107,7 +1110,8 @@ int gs_pge_bn1_tsum_f64(int32_t n, int32_t h, const float* Pa, const float* Pb, 
   double* tsum = reinterpret_cast<double*>(work);
   const float* Ga = reinterpret_cast<const float*>(tsum + 2 * h);
   const float* Gb = Ga + (int64_t)n * h;
-  pf::bn1_tsum_kernel<<<(h + 31) / 32, 256, 0, as_stream(stream)>>>(n, h, Pa, Pb, col_mean, rstd1, Ga, Gb, tsum);
+  const int splits = n >= 512 ? 16 : (n >= 64 ? 4 : 1);
+  pf::bn1_tsum_kernel<<<dim3((h + 31) / 32, splits), 256, 0, as_stream(stream)>>>(n, h, Pa, Pb, col_mean, rstd1, Ga, Gb, tsum);
   return finish_launch("pge_bn1_tsum");
 }
 

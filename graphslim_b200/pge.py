@@ -209,14 +209,15 @@ class PGE:
             K.pge_fused_l2_bwd_dx(Pa, Pb, i0, n_i, bn1, W2, Y2, dE, bn2, w3, s1, s2, count, work=work)
         with K.timed("pge_l2_bwd_dw"):
             dW2 = K.pge_fused_l2_bwd_dw(Pa, Pb, i0, n_i, bn1, Y2, dE, bn2, w3, s1, s2, count)
-        K.pge_bn1_tsum(Pa, Pb, cm1, rstd1, work)
         if sh is not None:
-            dist.all_reduce(work[:2 * h], group=sh["group"])                  # t1, t2 (float64)
+            # one collective: Ga, Gb and dW2 (float32).  The BN1 sums t1, t2 are linear in Ga / Gb, so they are formed
+            # from the reduced tiles afterwards (replicated, tiny) instead of travelling as a second all-reduce
             red = torch.cat([work[2 * h:].view(torch.float32), dW2.view(-1)])
-            dist.all_reduce(red, group=sh["group"])                           # Ga, Gb and dW2 (float32)
+            dist.all_reduce(red, group=sh["group"])
             nfl = 2 * n * h
             work[2 * h:].view(torch.float32).copy_(red[:nfl])
             dW2 = red[nfl:].view(h, h)
+        K.pge_bn1_tsum(Pa, Pb, cm1, rstd1, work)
         dPa, dPb, dgamma1, dbeta1 = K.pge_bn1_bwd_final(Pa, Pb, rstd1, self.gamma[0], cm1, work)
         dW1 = K.empty(h, 2 * d)
         K.gemm(dPa, x, ta=True, out=dW1[:, :d])

@@ -562,9 +562,9 @@ int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, c
 // L2-resident column tiling for X larger than the L2 (Reddit shape: 233 K rows x 602 floats = 561 MB against 126 MB):
 // the product is run tile_cols columns at a time, so the gathered slice X[:, c0:c0+tile_cols] (n_src x tile_cols x 4 B,
 // chosen by the caller to fit the L2) stays resident while every row sweeps it; each pass re-reads the 8 B / nnz of
-// (col, val) but the 4 F B / nnz of gathered feature rows come from the L2 instead of HBM.  Slices of >= 128 floats give the bits
-// of the untiled call (every output element accumulates its non-zeros in CSR order); narrower slices run the split-warp
-// kernel and agree to fp32 reassociation.
+// (col, val) but the 4 F B / nnz of gathered feature rows come from the L2 instead of HBM.  Full slices of >= 128 floats give
+// the bits of the untiled call (every output element accumulates its non-zeros in CSR order); narrower slices (and a
+// narrower remainder) run the split-warp kernel and agree to fp32 reassociation.
 int gs_spmm_csr_tiled_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
                           int64_t ldx, int32_t F, float* Y, int64_t ldy, int accumulate, int32_t n_chunks,
                           int32_t long_thr, const int32_t* chunk_row, const int32_t* chunk_beg,

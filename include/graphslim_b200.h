@@ -54,7 +54,7 @@ int gs_spmm_csr_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, c
 
 /* The same product run `tile_cols` feature columns at a time (a multiple of 4; the caller sizes n_src * tile_cols * 4 B
  * to fit the L2), for X larger than the L2: the gathered column slice stays L2-resident while the rows sweep it, at the
- * price of re-reading (col, val) once per slice.  Bit-identical to gs_spmm_csr_f32 for tile_cols >= 128, equal up to fp32 reassociation below. */
+ * price of re-reading (col, val) once per slice.  Equal to gs_spmm_csr_f32 up to fp32 reassociation (bit-identical on full slices of >= 128 floats). */
 int gs_spmm_csr_tiled_f32(int32_t n_rows, const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
                           int64_t ldx, int32_t F, float* Y, int64_t ldy, int accumulate, int32_t n_chunks,
                           int32_t long_thr, const int32_t* chunk_row, const int32_t* chunk_beg,

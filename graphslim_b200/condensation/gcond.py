@@ -95,10 +95,14 @@ class GCond(GCondBase):
             if self.x_variant:
                 pge_grads, feat_grad = None, dX
             else:
+                # only one optimiser steps per outer step (gcond.py:58-61): the half of the PGE backward feeding the other
+                # one is dead work (the reference computes it and zeroes it unread); traced runs keep both
+                pge_turn = self.one_step or self._pge_turn(it, ol)
+                both = self.one_step or self.trace is not None
                 with K.timed("phase_pge_backward"):
                     dA_raw = K.dense_gcn_norm_bwd(dA, self.adj_syn, r_norm)
-                    pge_grads, dX_pge = pge.backward(dA_raw)
-                    feat_grad = K.axpby(1.0, dX_pge, 1.0, dX)
+                    pge_grads, dX_pge = pge.backward(dA_raw, need_params=both or pge_turn, need_dx=both or not pge_turn)
+                    feat_grad = K.axpby(1.0, dX_pge, 1.0, dX) if dX_pge is not None else None
             if self.trace:
                 self.trace("grads", step=(it, ol), loss=loss, feat_grad=feat_grad, pge_grads=pge_grads)
             with K.timed("phase_optimizer"):

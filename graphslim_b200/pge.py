@@ -182,7 +182,7 @@ class PGE:
             return full
         return torch.cat([full[r * sh["pad"]: r * sh["pad"] + sh["rows"][r]] for r in range(sh["world"])])
 
-    def _backward_fused(self, dA):
+    def _backward_fused(self, dA, need_params=True, need_dx=True):
         """Backward of `_forward_fused`: dY2 is recomputed from Y2 inside the producers of both layer-2 products, dH1 is
         masked and reduced in the epilogue of the first, dW2 accumulates in TMEM in the second."""
         K, n, d, h = self.K, self.n, self.d, self.h
@@ -207,26 +207,33 @@ class PGE:
         work = K.pge_bn1_work(n, h)
         with K.timed("pge_l2_bwd_dx"):
             K.pge_fused_l2_bwd_dx(Pa, Pb, i0, n_i, bn1, W2, Y2, dE, bn2, w3, s1, s2, count, work=work)
-        with K.timed("pge_l2_bwd_dw"):
-            dW2 = K.pge_fused_l2_bwd_dw(Pa, Pb, i0, n_i, bn1, Y2, dE, bn2, w3, s1, s2, count)
+        dW2 = None
+        if need_params:
+            with K.timed("pge_l2_bwd_dw"):
+                dW2 = K.pge_fused_l2_bwd_dw(Pa, Pb, i0, n_i, bn1, Y2, dE, bn2, w3, s1, s2, count)
         if sh is not None:
-            # one collective: Ga, Gb and dW2 (float32).  The BN1 sums t1, t2 are linear in Ga / Gb, so they are formed
+            # one collective: Ga, Gb (and dW2), float32.  The BN1 sums t1, t2 are linear in Ga / Gb, so they are formed
             # from the reduced tiles afterwards (replicated, tiny) instead of travelling as a second all-reduce
-            red = torch.cat([work[2 * h:].view(torch.float32), dW2.view(-1)])
-            dist.all_reduce(red, group=sh["group"])
             nfl = 2 * n * h
-            work[2 * h:].view(torch.float32).copy_(red[:nfl])
-            dW2 = red[nfl:].view(h, h)
+            flt = work[2 * h:].view(torch.float32)
+            red = torch.cat([flt, dW2.view(-1)]) if need_params else flt
+            dist.all_reduce(red, group=sh["group"])
+            if need_params:
+                flt.copy_(red[:nfl])
+                dW2 = red[nfl:].view(h, h)
         K.pge_bn1_tsum(Pa, Pb, cm1, rstd1, work)
         dPa, dPb, dgamma1, dbeta1 = K.pge_bn1_bwd_final(Pa, Pb, rstd1, self.gamma[0], cm1, work)
-        dW1 = K.empty(h, 2 * d)
-        K.gemm(dPa, x, ta=True, out=dW1[:, :d])
-        K.gemm(dPb, x, ta=True, out=dW1[:, d:])
-        dX = K.gemm(dPa, W1[:, :d])
-        K.gemm(dPb, W1[:, d:], out=dX, beta=1.0)
-        zeros_h = K.zeros(h)
-        grads = [dW1, zeros_h, dW2, zeros_h.clone(), dw3.reshape(1, h), db3.reshape(1), dgamma1, dbeta1, dgamma2,
-                 dbeta2]
+        grads = dX = None
+        if need_params:
+            dW1 = K.empty(h, 2 * d)
+            K.gemm(dPa, x, ta=True, out=dW1[:, :d])
+            K.gemm(dPb, x, ta=True, out=dW1[:, d:])
+            zeros_h = K.zeros(h)
+            grads = [dW1, zeros_h, dW2, zeros_h.clone(), dw3.reshape(1, h), db3.reshape(1), dgamma1, dbeta1, dgamma2,
+                     dbeta2]
+        if need_dx:
+            dX = K.gemm(dPa, W1[:, :d])
+            K.gemm(dPb, W1[:, d:], out=dX, beta=1.0)
         self._saved = None
         return grads, dX
 
@@ -268,10 +275,14 @@ class PGE:
         return self.forward(x, keep=keep)
 
     # ---------------------------------------------------------------------------------- backward
-    def backward(self, dA):
-        """Returns (grads in parameters() order, dX)."""
+    def backward(self, dA, need_params=True, need_dx=True):
+        """Returns (grads in parameters() order, dX).  `need_params=False` / `need_dx=False` let the caller skip the half
+        of the backward whose result it will discard: the reference back-propagates into both the PGE parameters and
+        feat_syn on every outer step but steps only one optimiser (gcond.py:54-61) and zeroes the other gradient
+        unread, so the N'^2-deep dW2 product (and the layer-1 weight products) are dead work on feature turns.  The
+        fused path honours the flags (returns None for the skipped half); the other paths compute everything."""
         if self._saved[6] is None:                               # saved by the fused forward: H1 was never materialised
-            return self._backward_fused(dA)
+            return self._backward_fused(dA, need_params, need_dx)
         if getattr(self, "shard", None) is not None:
             return self._backward_sharded(dA)
         K, n, d, h = self.K, self.n, self.d, self.h

@@ -180,3 +180,24 @@ def check_against_golden(gold, sub, args, data, agent, seen, pge_init, first_tol
 @pytest.mark.parametrize("name", FAST)
 def test_product_host_logic_matches_reference(name, emulated):
     check_against_golden(*run_case(name), **helpers.parity_tol(name, 0))
+
+
+def test_skipping_the_unused_half_of_the_pge_backward_changes_nothing(emulated):
+    """gcond.py:54-61 steps one optimiser per outer step; the product skips the half of the PGE backward that feeds the
+    other one (dW2 / dW1 on feature turns, dX on PGE turns) unless a trace hook asks for both.  Same final state."""
+    name = "mini_sgc1_trans"                                   # 12 epochs: PGE turns (it < 10) and feature turns
+
+    def final(traced):
+        args = helpers.case_args(name, save_init=False, progress=False)
+        raw = helpers.case_graph(name)
+        data = gdata.TransAndInd(raw, args.dataset, args.pre_norm)
+        helpers.seed_everything(args.seed)
+        agent = create_reducer(args.method, setting=args.setting, data=data, args=args)
+        if traced:
+            agent.trace = lambda kind, **kw: None
+        agent.reduce(data, verbose=False)
+        return agent.feat_syn.clone(), torch.cat([p.reshape(-1) for p in agent.pge.parameters()])
+
+    f0, p0 = final(True)
+    f1, p1 = final(False)
+    assert torch.equal(f0, f1) and torch.equal(p0, p1)

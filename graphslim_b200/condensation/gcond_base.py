@@ -19,8 +19,14 @@ from ..sampler import ClassSampler, DeviceClassSampler
 
 
 def _kernels(device, args):
-    """The only compute backend: CUDA kernels from libgraphslim_b200.so (raises on CPU / missing library)."""
-    return CudaOps(device, precision=int(getattr(args, "gemm_precision", 1)))
+    """The only compute backend: CUDA kernels from libgraphslim_b200.so (raises on CPU / missing library).
+    Optional switches (default on): args.pge_fused -- the fused tcgen05 PGE pipeline (csrc/pge_fused.cu);
+    args.grouped_mn -- the TMA-fed MN-major grouped products of the real side (csrc/grouped_tn.cu; they flush a class's
+    partial sums from several CTAs with float atomics, so two runs differ in the last bits)."""
+    K = CudaOps(device, precision=int(getattr(args, "gemm_precision", 1)))
+    K.pge_fused = bool(getattr(args, "pge_fused", True))
+    K.grouped_mn = bool(getattr(args, "grouped_mn", True))
+    return K
 
 
 class _Adam:

@@ -48,5 +48,27 @@ def main():
     print(json.dumps(out))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--forward" not in sys.argv:
     main()
+
+
+def forward_probe():
+    """The two forward products of the real side at the arxiv shape, tensor-core (3xBF16) vs fp32 SIMT."""
+    R, d, h, C = 40 * 3840, 128, 256, 40
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.randn(R, d, device="cuda", generator=gen)
+    W1 = torch.randn(d, h, device="cuda", generator=gen)
+    b1 = torch.randn(h, device="cuda", generator=gen)
+    W2 = torch.randn(h, C, device="cuda", generator=gen)
+    b2 = torch.randn(C, device="cuda", generator=gen)
+    out = {}
+    for prec in (1, 0):
+        K = CudaOps("cuda", precision=prec)
+        H1 = K.gemm(X, W1, bias=b1, relu=True)
+        out[f"ms_H1_p{prec}"] = timeit(lambda: K.gemm(X, W1, bias=b1, relu=True))
+        out[f"ms_U_p{prec}"] = timeit(lambda: K.gemm(H1, W2, bias=b2))
+    print(json.dumps(out))
+
+
+if __name__ == "__main__" and "--forward" in sys.argv:
+    forward_probe()

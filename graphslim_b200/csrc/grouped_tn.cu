@@ -207,32 +207,33 @@ grouped_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         constexpr int kIters = KR / kRowStep;
         const float* side = reinterpret_cast<const float*>(region_b + C::kB);
         const int c = bc16 * 4, cb = bc16 >> 4, c4 = bc16 & 15;
-        float4 h1[kIters], acc[kIters];
+        float4 h1[kIters];
+        float2 acc_lo[kIters], acc_hi[kIters];          // packed pairs: one FFMA2 (fma.rn.f32x2) per two columns
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
           const int row = row0 + brbase + kRowStep * i;
           h1[i] = (row < p.total_rows && c < p.N) ? ld4(p.H1 + (int64_t)row * p.ldh + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          acc_lo[i] = acc_hi[i] = make_float2(0.f, 0.f);
         }
         for (int k = 0; k < p.Cw; ++k) {
           const float4 w = *reinterpret_cast<const float4*>(w2t + k * (64 * BSUB) + c);
+          const float2 w_lo = make_float2(w.x, w.y), w_hi = make_float2(w.z, w.w);
 #pragma unroll
           for (int i = 0; i < kIters; ++i) {
             const float du = side[(brbase + kRowStep * i) * p.Cw + k];
-            acc[i].x = fmaf(du, w.x, acc[i].x);
-            acc[i].y = fmaf(du, w.y, acc[i].y);
-            acc[i].z = fmaf(du, w.z, acc[i].z);
-            acc[i].w = fmaf(du, w.w, acc[i].w);
+            const float2 du2 = make_float2(du, du);
+            acc_lo[i] = __ffma2_rn(du2, w_lo, acc_lo[i]);
+            acc_hi[i] = __ffma2_rn(du2, w_hi, acc_hi[i]);
           }
         }
         uint8_t* hi = region_b + cb * kSub;
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
           float4 o;
-          o.x = h1[i].x > 0.f ? acc[i].x : 0.f;
-          o.y = h1[i].y > 0.f ? acc[i].y : 0.f;
-          o.z = h1[i].z > 0.f ? acc[i].z : 0.f;
-          o.w = h1[i].w > 0.f ? acc[i].w : 0.f;
+          o.x = h1[i].x > 0.f ? acc_lo[i].x : 0.f;
+          o.y = h1[i].y > 0.f ? acc_lo[i].y : 0.f;
+          o.z = h1[i].z > 0.f ? acc_hi[i].x : 0.f;
+          o.w = h1[i].w > 0.f ? acc_hi[i].y : 0.f;
           gbsum.x += o.x; gbsum.y += o.y; gbsum.z += o.z; gbsum.w += o.w;
           store_split4<C::kWithLo>(hi, sw128_offset(brbase + kRowStep * i, c4 * 4), o);
         }

@@ -26,6 +26,7 @@
 // fp32 accumulation in TMEM.  Warp roles (14 warps, one persistent CTA per SM): 0-7 producers, 8-11 epilogue
 // (TMEM lane quarter = warp % 4), 12 MMA issuer (one lane), 13 TMA issuer (one lane).
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -244,15 +245,17 @@ struct FwdParams {
   double* stats;             // [sum y (H) | sum y^2 (H)], accumulated with atomics
 };
 
-// Warp roles of the forward: 4 producer warps (generating H1 is light), 8 epilogue warps (two per TMEM lane quarter,
-// alternating 32-column blocks: the epilogue -- TMEM read, transposition, Y2 store, column sums -- is what bounds this
-// kernel), the MMA issuer and the TMA issuer.
-constexpr int kFwdProducerWarps = 4;
+// Warp roles of the forward (18 warps): 8 producer warps, 8 epilogue warps (two per TMEM lane quarter, alternating
+// 32-column blocks), the MMA issuer and the TMA issuer.  ncu showed the 4-warp epilogue (v1) and then the 4-warp producer
+// (v2: exposed L2 latency of the Pb rows) starving the tensor pipe in turn; both roles get 8 warps.
+constexpr int kFwdProducerWarps = 8;
 constexpr int kFwdEpiWarps = 8;
+constexpr int kFwdMmaWarp = 16, kFwdTmaWarp = 17;
+constexpr int kFwdThreads = 18 * 32;
 constexpr uint32_t kFwdStagingBytes = kFwdEpiWarps * 32 * 32 * 4;     // dense swizzled 32 x 32 tiles, one per warp
 
 template <int H, int NPASS>
-__global__ void __launch_bounds__(kThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
   using C = Cfg<H, NPASS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
   cta_range(p.g.num_tiles, t0, t1);
 
   if (threadIdx.x == 0) init_bars<C::kStages>(bars, kFwdProducerWarps + 1, kFwdEpiWarps * 32);
-  if (warp == kMmaWarp) tmem_alloc(smem_u32(&bars.tmem_holder), C::kTmemCols);
+  if (warp == kFwdMmaWarp) tmem_alloc(smem_u32(&bars.tmem_holder), C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -272,9 +275,10 @@ __global__ void __launch_bounds__(kThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
 
   if (warp < kFwdProducerWarps) {
     // ============================== producers: generate the H1 tile ==============================
-    // thread = (c4, jl): tile rows u = jl + 8 il for all 16 il; one Pa vector, 16 Pb vectors per k-block
+    // thread = (c4, jl, ilb): tile rows u = jl + 8 il for il = ilb + 2 i; one Pa vector and 8 Pb vectors per k-block, all
+    // requested before the stage wait so their L2 latency overlaps it
     const int tid = threadIdx.x;
-    const int c4 = tid & 15, jl = tid >> 4;
+    const int c4 = tid & 15, jl = (tid >> 4) & 7, ilb = tid >> 7;
     uint32_t it = 0;
     for (int t = t0; t < t1; ++t) {
       const int ib = t / p.g.tiles_j, jb = t - ib * p.g.tiles_j;
@@ -290,32 +294,28 @@ __global__ void __launch_bounds__(kThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
         const float4 pa = ld4(pa_row + c);
         float4 pb[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pb[i] = ld4(pb_rows + (int64_t)(i < ni ? i : 0) * H + c);
+        for (int i = 0; i < 8; ++i) {
+          const int il = ilb + 2 * i;
+          pb[i] = ld4(pb_rows + (int64_t)(il < ni ? il : 0) * H + c);
+        }
         const int s = it % C::kStages;
         const uint32_t ph = (it / C::kStages) & 1;
         mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1);
         uint8_t* sa_hi = smem + s * C::kStageBytes;
         uint8_t* sa_lo = sa_hi + kPlaneA;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (half == 1) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pb[i] = ld4(pb_rows + (int64_t)(8 + i < ni ? 8 + i : 0) * H + c);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int il = half * 8 + i;
-            float4 o = h1_value4(pa, pb[i], k1);
-            if (!(jv && il < ni)) o = make_float4(0.f, 0.f, 0.f, 0.f);
-            store_split4<C::kWithLo>(sa_hi, sa_lo, sw128_offset(il * BJ + jl, c4 * 4), o);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int il = ilb + 2 * i;
+          float4 o = h1_value4(pa, pb[i], k1);
+          if (!(jv && il < ni)) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          store_split4<C::kWithLo>(sa_hi, sa_lo, sw128_offset(il * BJ + jl, c4 * 4), o);
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars.full[s]));
       }
     }
-  } else if (warp == kTmaWarp) {
+  } else if (warp == kFwdTmaWarp) {
     // ============================== TMA: the W2 image block of every k-block ==============================
     if (lane == 0) {
       uint32_t it = 0;
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kFwdMmaWarp) {
     mma_role_rowtiles<H, NPASS>(smem, bars, tmem_base, t0, t1, lane);
   } else {
     // ============================== epilogue: store Y2, accumulate its column sums ==============================
@@ -422,9 +422,238 @@ __global__ void __launch_bounds__(kThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kFwdMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// =============================================================================================================
+// forward on CTA PAIRS (cta_group::2): one UMMA of M = 256 covers the tiles of both SMs of a TPC; each CTA keeps ITS HALF
+// of the W2 image (128 of the 256 operand rows, all k-blocks, hi + lo planes: 128 KB) resident in shared memory for the
+// whole kernel.  Against the single-CTA kernel this removes the 64 KB W2 refill per k-block and halves the B bytes an
+// UMMA reads from shared memory (the single-CTA kernels are bound by shared-memory bandwidth).
+// =============================================================================================================
+template <int H, int NPASS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) pge_l2_fwd2_kernel(FwdParams p) {
+  using C = Cfg<H, NPASS>;
+  constexpr int kFwdProducerWarps = 4;                  // this variant keeps the 14-warp layout (4 + 8 + MMA + TMA)
+  constexpr int kStages2 = 2;
+  constexpr uint32_t kBHalfPlane = (H / 2) * BK * 2;                      // one plane of this CTA's half of a k-block
+  constexpr uint32_t kBHalf = C::KB * C::kPlanes * kBHalfPlane;           // resident: 128 KB at H = 256, 3 passes
+  constexpr uint32_t kIdesc2 = make_idesc_bf16(256, H, 0, 0);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sB = smem;                                                     // [kb][plane][H/2 rows x 128 B]
+  uint8_t* sA = smem + kBHalf;                                            // kStages2 x (hi | lo) A tiles
+  float* staging = reinterpret_cast<float*>(sA + kStages2 * kStageA);
+  __shared__ __align__(8) PipeBars bars;
+  __shared__ __align__(8) uint64_t bar_bload;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int num_st = (p.g.num_tiles + 1) >> 1;                            // super tiles: tiles (2 st, 2 st + 1)
+  const int st0 = (int)(((int64_t)num_st * pair) / npairs), st1 = (int)(((int64_t)num_st * (pair + 1)) / npairs);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(smem_u32(&bars.full[s]), 2 * kFwdProducerWarps);          // leader's copy: producers of both CTAs
+      mbar_init(smem_u32(&bars.empty[s]), 1);                             // multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&bars.tfull[a]), 1);                             // multicast commit
+      mbar_init(smem_u32(&bars.tempty[a]), 2 * kFwdEpiWarps * 32);        // leader's copy: epilogue threads of both CTAs
+    }
+    mbar_init(smem_u32(&bar_bload), 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc_2cta(smem_u32(&bars.tmem_holder), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == kTmaWarp && lane == 0) {
+    // this CTA's half of the W2 image: rows [rank * H/2, +H/2) of every (k-block, plane) slab
+    const uint32_t bar = smem_u32(&bar_bload);
+    mbar_arrive_expect_tx(bar, kBHalf);
+    for (int kb = 0; kb < C::KB; ++kb)
+      for (int pl = 0; pl < C::kPlanes; ++pl)
+        bulk_g2s(smem_u32(sB + (kb * C::kPlanes + pl) * kBHalfPlane),
+                 p.Bimg + (size_t)(kb * C::kPlanes + pl) * C::kPlaneB + (size_t)rank * kBHalfPlane, kBHalfPlane, bar);
+  }
+  mbar_wait(smem_u32(&bar_bload), 0);
+  cluster_sync_all();                                   // both halves of B resident, both CTAs' barriers initialised
+  const uint32_t tmem_base = bars.tmem_holder;
+
+  if (warp < kFwdProducerWarps) {
+    const int tid = threadIdx.x;
+    const int c4 = tid & 15, jl = tid >> 4;
+    uint32_t it = 0;
+    for (int st = st0; st < st1; ++st) {
+      const int t = 2 * st + (int)rank;                 // may be one past the last tile: generated as zeros
+      const int ib = t / p.g.tiles_j, jb = t - ib * p.g.tiles_j;
+      const int j = jb * BJ + jl;
+      const int ni = min(BI, p.g.n_i - ib * BI);        // <= 0 for the phantom tile
+      const bool jv = j < p.g.n && ni > 0;
+      const float* pa_row = p.Pa + (int64_t)(jv ? j : 0) * H;
+      const float* pb_rows = p.Pb + (int64_t)(p.g.i_first + (ni > 0 ? ib * BI : 0)) * H;
+#pragma unroll 1
+      for (int kb = 0; kb < C::KB; ++kb, ++it) {
+        const int c = kb * BK + c4 * 4;
+        const H1Consts k1 = load_h1_consts(p.bn1, c);
+        const float4 pa = ld4(pa_row + c);
+        float4 pb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pb[i] = ld4(pb_rows + (int64_t)(i < ni ? i : 0) * H + c);
+        const int s = it % kStages2;
+        const uint32_t ph = (it / kStages2) & 1;
+        mbar_wait_cluster(smem_u32(&bars.empty[s]), ph ^ 1);
+        uint8_t* sa_hi = sA + s * kStageA;
+        uint8_t* sa_lo = sa_hi + kPlaneA;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pb[i] = ld4(pb_rows + (int64_t)(8 + i < ni ? 8 + i : 0) * H + c);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int il = half * 8 + i;
+            float4 o = h1_value4(pa, pb[i], k1);
+            if (!(jv && il < ni)) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            store_split4<C::kWithLo>(sa_hi, sa_lo, sw128_offset(il * BJ + jl, c4 * 4), o);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&bars.full[s]), 0);      // the leader's barrier
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (rank == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int st = st0; st < st1; ++st, ++tcount) {
+        const int acc = tcount & 1;
+        const uint32_t acc_ph = (tcount >> 1) & 1;
+        mbar_wait_cluster(smem_u32(&bars.tempty[acc]), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * H);
+        for (int kb = 0; kb < C::KB; ++kb, ++it) {
+          const int s = it % kStages2;
+          const uint32_t ph = (it / kStages2) & 1;
+          mbar_wait_cluster(smem_u32(&bars.full[s]), ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa_hi = smem_u32(sA + s * kStageA);
+            const uint32_t sa_lo = sa_hi + kPlaneA;
+            const uint32_t sb_hi = smem_u32(sB + (kb * C::kPlanes) * kBHalfPlane);
+            const uint32_t sb_lo = sb_hi + kBHalfPlane;
+#pragma unroll
+            for (int pass = 0; pass < NPASS; ++pass) {
+              const uint32_t a_base = (pass == 2) ? sa_lo : sa_hi;
+              const uint32_t b_base = (pass == 1) ? sb_lo : sb_hi;
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk) {
+                umma_bf16_2cta(tmem_d, make_desc_k_sw128(a_base + kk * 32), make_desc_k_sw128(b_base + kk * 32), kIdesc2,
+                               (kb | pass | kk) ? 1u : 0u);
+              }
+            }
+            umma_commit_2cta(smem_u32(&bars.empty[s]));          // frees the stage in both CTAs
+          }
+          __syncwarp();
+        }
+        if (lane == 0) umma_commit_2cta(smem_u32(&bars.tfull[acc]));
+        __syncwarp();
+      }
+    }
+  } else if (warp == kTmaWarp) {
+    // nothing to stream: B is resident
+  } else {
+    constexpr int NBW = C::NB / 2;
+    const int ew = warp - kFwdProducerWarps;
+    const int q = warp & 3, half = ew >> 2;
+    float* st_ = staging + ew * (32 * 32);
+    float ps1[NBW], ps2[NBW];
+    double d1[NBW], d2[NBW];
+#pragma unroll
+    for (int b = 0; b < NBW; ++b) {
+      ps1[b] = ps2[b] = 0.f;
+      d1[b] = d2[b] = 0.0;
+    }
+    uint32_t tcount = 0;
+    const int ch = lane & 7, rsub = lane >> 3;
+    for (int st = st0; st < st1; ++st, ++tcount) {
+      const int t = 2 * st + (int)rank;
+      const int ib = t / p.g.tiles_j, jb = t - ib * p.g.tiles_j;
+      const int acc = tcount & 1;
+      const uint32_t acc_ph = (tcount >> 1) & 1;
+      mbar_wait_cluster(smem_u32(&bars.tfull[acc]), acc_ph);
+      tc_fence_after();
+#pragma unroll
+      for (int bi = 0; bi < NBW; ++bi) {
+        const int b = 2 * bi + half;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + b * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jc = 0; jc < 8; ++jc)
+          *reinterpret_cast<float4*>(st_ + lane * 32 + ((jc ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(r[4 * jc]), __uint_as_float(r[4 * jc + 1]), __uint_as_float(r[4 * jc + 2]),
+                          __uint_as_float(r[4 * jc + 3]));
+        __syncwarp();
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const float x = st_[u * 32 + ((((lane >> 2) ^ (u & 7)) << 2) | (lane & 3))];
+          a1 += x;
+          a2 = fmaf(x, x, a2);
+        }
+        ps1[bi] += a1;
+        ps2[bi] += a2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int row = rsub + 4 * k, u = q * 32 + row;
+          const int li = ib * BI + (u >> 3), j = jb * BJ + (u & 7);
+          if (li < p.g.n_i && j < p.g.n)
+            *reinterpret_cast<float4*>(p.Y2 + ((int64_t)li * p.g.n + j) * H + b * 32 + ch * 4) =
+                *reinterpret_cast<const float4*>(st_ + row * 32 + ((ch ^ (row & 7)) << 2));
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(smem_u32(&bars.tempty[acc]), 0);
+      if ((tcount & 7) == 7) {
+#pragma unroll
+        for (int b = 0; b < NBW; ++b) {
+          d1[b] += (double)ps1[b];
+          d2[b] += (double)ps2[b];
+          ps1[b] = ps2[b] = 0.f;
+        }
+      }
+    }
+    double* red = reinterpret_cast<double*>(staging);
+    named_bar_sync(1, kFwdEpiWarps * 32);
+#pragma unroll
+    for (int b = 0; b < NBW; ++b) {
+      red[((ew * NBW + b) * 2 + 0) * 32 + lane] = d1[b] + (double)ps1[b];
+      red[((ew * NBW + b) * 2 + 1) * 32 + lane] = d2[b] + (double)ps2[b];
+    }
+    named_bar_sync(1, kFwdEpiWarps * 32);
+    for (int idx = ew * 32 + lane; idx < 2 * H; idx += kFwdEpiWarps * 32) {
+      const int stat = idx / H, col = idx % H;
+      const int b = col >> 5, l = col & 31;
+      double v = 0.0;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) v += red[((((b & 1) * 4 + qq) * NBW + (b >> 1)) * 2 + stat) * 32 + l];
+      atomicAdd(p.stats + idx, v);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                   // the peer's barriers / TMEM stay valid until both are done
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, C::kTmemCols);
   }
 }
 
@@ -969,8 +1198,23 @@ static int launch_fwd(FwdParams& p, cudaStream_t st) {
     if (rc) return rc;
     configured = true;
   }
+  static const int two_cta = [] {
+    const char* e = getenv("GS_PGE_2CTA");
+    return e ? atoi(e) : 0;
+  }();
+  if (two_cta && p.g.num_tiles >= 2 * kNumSMs) {
+    constexpr size_t smem2 = (size_t)C::KB * C::kPlanes * (H / 2) * BK * 2 + 2 * kStageA + kFwdStagingBytes + 1024;
+    static bool configured2 = false;
+    if (!configured2) {
+      const int rc = set_smem(pge_l2_fwd2_kernel<H, NPASS>, smem2, "cudaFuncSetAttribute(pge_l2_fwd2)");
+      if (rc) return rc;
+      configured2 = true;
+    }
+    pge_l2_fwd2_kernel<H, NPASS><<<kNumSMs, kThreads, smem2, st>>>(p);
+    return finish_launch("pge_l2_fwd2");
+  }
   const int grid = p.g.num_tiles < kNumSMs ? p.g.num_tiles : kNumSMs;
-  pge_l2_fwd_kernel<H, NPASS><<<grid, kThreads, smem, st>>>(p);
+  pge_l2_fwd_kernel<H, NPASS><<<grid, kFwdThreads, smem, st>>>(p);
   return finish_launch("pge_l2_fwd");
 }
 

@@ -1,4 +1,5 @@
 """GCond on B200: drop-in for graphslim.condensation.gcond.GCond (same ctor / ``reduce(data, verbose)``)."""
+import os
 import time
 
 import torch
@@ -45,7 +46,8 @@ class GCond(GCondBase):
         self.inner = InnerLoop(K, self.model, self.feat_syn, self.nnodes_syn, args.lr, outer_loop * inner_loop,
                                use_graph=getattr(args, "cuda_graphs", True) and self.trace is None)
         self.match_graph = MatchGraph(K, self.model, self.feat_syn, args.dis_metric,
-                                      use_graph=getattr(args, "cuda_graphs", True) and self.trace is None)
+                                      use_graph=getattr(args, "cuda_graphs", True) and self.trace is None,
+                                      overlap=getattr(args, "overlap_syn", os.environ.get("GS_OVERLAP_SYN", "1") != "0"))
         self.loss_avg, self.best_val = 0, 0
         self.adj_syn_inner = None
         self._pge_ready = None

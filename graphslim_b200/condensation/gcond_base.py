@@ -138,50 +138,93 @@ def _capture(K, graph, body):
 
 class MatchGraph:
     """The fixed-shape middle of an outer step -- synthetic forward, first-order gradients, matching distance and the
-    second-order backward (gcond_base.py:210-239 for all classes at once, ~90 small launches) -- captured once in a CUDA
-    graph and replayed.  Inputs that are fresh tensors every step (the real-side class-column gradients, the normalised
-    adjacency) are copied into fixed buffers first; loss, dX and dA come back in the graph's own fixed outputs, which
-    the caller consumes before the next replay.  First call eager (lazy kernel configuration, workspace growth), second
-    call captures, later calls replay; a failed capture falls back to the step-by-step path for good."""
+    second-order backward (gcond_base.py:210-239 for all classes at once, ~90 small launches) -- captured once in two
+    CUDA graphs and replayed.  The first half (forward + first-order gradients) does not depend on the real side, so
+    `start` replays it on a side stream while the caller samples and computes the real-side gradients (a host-bound
+    sequence of variable-shape launches) on the main stream; `finish` joins the streams and replays the second half
+    (matching + second-order backward).  Inputs that are fresh tensors every step (the real-side class-column
+    gradients, the normalised adjacency) are copied into fixed buffers first; loss, dX and dA come back in the graph's
+    own fixed outputs, which the caller consumes before the next replay.  The side stream's products pack their B
+    operand into a workspace of their own (K._ws is only safe in stream order).  First call eager (lazy kernel
+    configuration, workspace growth), second call captures, later calls replay; a failed capture falls back to the
+    step-by-step path for good."""
 
-    def __init__(self, K, model, feat_syn, metric, use_graph=True):
+    def __init__(self, K, model, feat_syn, metric, use_graph=True, overlap=True):
         self.K, self.model, self.feat, self.metric = K, model, feat_syn, metric
         self.use_graph = bool(use_graph) and torch.device(K.device).type == "cuda"
-        self.graph, self.calls, self.replays = None, 0, 0
-        self.gr = self.adj = self.out = None
+        self.overlap = bool(overlap)
+        self.graph, self.graph_fwd, self.calls, self.replays = None, None, 0, 0
+        self.gr = self.adj = self.out = self.side = self._pending = None
 
-    def _body(self, gr, adj, need_dA):
+    def _fwd(self, adj):
+        self.model.syn_forward(self.feat, adj)
+        self._gs = self.model.syn_grads()
+
+    def _bwd(self, gr, need_dA):
         K, model = self.K, self.model
-        model.syn_forward(self.feat, adj)
-        gs = model.syn_grads()
         loss = K.zeros(1)
-        G = K.match(gs, gr, model.widths, model.is_bias, model.lay.coeff, self.metric, loss)
+        G = K.match(self._gs, gr, model.widths, model.is_bias, model.lay.coeff, self.metric, loss)
         dX, dA = model.syn_backward(G, need_dA=need_dA)
         return loss, dX, dA
 
-    def run(self, gr, adj, need_dA):
+    def _body(self, gr, adj, need_dA):
+        self._fwd(adj)
+        return self._bwd(gr, need_dA)
+
+    def start(self, adj, need_dA):
+        """Begin the step's synthetic forward (side stream) if the graphs exist; otherwise only remember the inputs."""
         self.calls += 1
+        self._pending = (adj, need_dA, False)
+        if not self.use_graph or self.graph is None:
+            return
+        if adj.data_ptr() != self.adj.data_ptr():
+            self.adj.copy_(adj)
+        if not self.overlap:
+            return
+        self.side.wait_stream(torch.cuda.current_stream(self.K.device))
+        with torch.cuda.stream(self.side):
+            self.graph_fwd.replay()
+        self._pending = (adj, need_dA, True)
+
+    def finish(self, gr):
+        K = self.K
+        adj, need_dA, started = self._pending
+        self._pending = None
         if not self.use_graph or self.calls == 1:
             return self._body(gr, adj, need_dA)
         if self.graph is None:
             self.gr = [g.clone() for g in gr]
             self.adj = adj.clone()
-            graph = torch.cuda.CUDAGraph()
+            g_fwd, g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            ws_main = getattr(K, "_ws", None)
             try:
-                self.out = _capture(self.K, graph, lambda: self._body(self.gr, self.adj, need_dA))
+                K._ws = torch.empty(ws_main.numel() if ws_main is not None else 1 << 22, dtype=torch.uint8,
+                                    device=K.device)
+                try:
+                    _capture(K, g_fwd, lambda: self._fwd(self.adj))
+                finally:
+                    self._side_ws, K._ws = K._ws, ws_main
+                self.out = _capture(K, g_bwd, lambda: self._bwd(self.gr, need_dA))
             except Exception as exc:
                 self.use_graph, self.capture_error = False, repr(exc)
-                torch.cuda.synchronize(self.K.device)
+                torch.cuda.synchronize(K.device)
                 return self._body(gr, adj, need_dA)
-            self.graph = graph
+            self.graph_fwd, self.graph = g_fwd, g_bwd
+            self.side = torch.cuda.Stream(K.device)
         else:
             for dst, src in zip(self.gr, gr):
                 dst.copy_(src)
-            if adj.data_ptr() != self.adj.data_ptr():
-                self.adj.copy_(adj)
+        if started:
+            torch.cuda.current_stream(K.device).wait_stream(self.side)
+        else:
+            self.graph_fwd.replay()
         self.graph.replay()
         self.replays += 1
         return self.out
+
+    def run(self, gr, adj, need_dA):
+        self.start(adj, need_dA)
+        return self.finish(gr)
 
 
 class GCondBase:
@@ -364,6 +407,10 @@ class GCondBase:
         """Returns (loss device scalar, dX, dA_hat, batch) for the current feat_syn / adj_syn / model weights.
         With class sharding (model.lay.mask) only the owned classes are sampled in full and matched."""
         K = self.K
+        mg = getattr(self, "match_graph", None)
+        use_mg = mg is not None and mg.use_graph and self.trace is None
+        if use_mg:
+            mg.start(self.adj_syn, not model.identity_adj)    # synthetic forward on a side stream, under the real side
         pf = getattr(self, "_prefetch", None)
         t0 = time.perf_counter()
         with K.timed("phase_sample_h2d"):
@@ -373,10 +420,9 @@ class GCondBase:
             self.trace("sample", rb=rb)
         with K.timed("phase_real_grads"):
             gr = model.real_grads(rb, self.features, self.ones_full, self.features_padded)
-        mg = getattr(self, "match_graph", None)
-        if mg is not None and mg.use_graph and self.trace is None:
-            with K.timed("phase_syn_graph"):                 # forward + gradients + matching + backward, one replay
-                loss, dX, dA = mg.run(gr, self.adj_syn, not model.identity_adj)
+        if use_mg:
+            with K.timed("phase_syn_graph"):                 # (forward + gradients) | matching + backward: two replays
+                loss, dX, dA = mg.finish(gr)
             return loss, dX, dA, rb
         with K.timed("phase_syn_forward_grads"):
             model.syn_forward(self.feat_syn, self.adj_syn)

@@ -87,24 +87,37 @@ __global__ void softmax_jvp_kernel(int rows, int C, const float* __restrict__ S,
 }
 
 // ---------------------------------------------------------------- gradient matching
-// One thread per column; threads of a warp read 32 consecutive columns of a row (coalesced).
-__global__ void match_col_stats_kernel(int rows, int cols, const float* __restrict__ gs_, const float* __restrict__ gr,
-                                       int64_t ld, float* __restrict__ stats, int64_t sld) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= cols) return;
+// 32 columns per CTA: lanes read 32 consecutive columns of a row (coalesced), the 8 warps interleave the rows and their
+// partial sums are added in warp order through shared memory (one thread per column with a serial row loop took 96 us
+// on the 500 x 1792 first-layer gradient of the Flickr shape: 14 CTAs, 500 dependent loads each).
+__global__ void __launch_bounds__(256) match_col_stats_kernel(int rows, int cols, const float* __restrict__ gs_,
+                                                              const float* __restrict__ gr, int64_t ld,
+                                                              float* __restrict__ stats, int64_t sld) {
+  __shared__ float red[4][8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   float dot = 0.f, ns = 0.f, nr = 0.f, sq = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    const float a = gs_[(int64_t)r * ld + j], b = gr[(int64_t)r * ld + j];
-    dot = fmaf(a, b, dot);
-    ns = fmaf(a, a, ns);
-    nr = fmaf(b, b, nr);
-    const float d = a - b;
-    sq = fmaf(d, d, sq);
+  if (j < cols) {
+    for (int r = w; r < rows; r += 8) {
+      const float a = gs_[(int64_t)r * ld + j], b = gr[(int64_t)r * ld + j];
+      dot = fmaf(a, b, dot);
+      ns = fmaf(a, a, ns);
+      nr = fmaf(b, b, nr);
+      const float d = a - b;
+      sq = fmaf(d, d, sq);
+    }
   }
-  stats[j] = dot;
-  stats[sld + j] = ns;
-  stats[2 * sld + j] = nr;
-  stats[3 * sld + j] = sq;
+  red[0][w][lane] = dot;
+  red[1][w][lane] = ns;
+  red[2][w][lane] = nr;
+  red[3][w][lane] = sq;
+  __syncthreads();
+  if (w < 4 && j < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += red[w][i][lane];
+    stats[(int64_t)w * sld + j] = v;
+  }
 }
 
 // One block per class.  metric 0 'ours', 1 'mse', 2 'cos'  (graphslim/condensation/utils.py:12-106)
@@ -418,7 +431,7 @@ int gs_match_col_stats_f32(int32_t rows, int32_t cols, const float* gs_, const f
                            int64_t stats_ld, void* stream) {
   GS_REQUIRE(rows >= 0 && cols >= 0 && gs_ && gr && stats && ld >= cols);
   if (cols == 0) return GS_OK;
-  match_col_stats_kernel<<<blocks_for(cols, 128), 128, 0, as_stream(stream)>>>(rows, cols, gs_, gr, ld, stats, stats_ld);
+  match_col_stats_kernel<<<(cols + 31) / 32, 256, 0, as_stream(stream)>>>(rows, cols, gs_, gr, ld, stats, stats_ld);
   return finish_launch("match_col_stats");
 }
 

@@ -263,6 +263,61 @@ def test_gemm_beta_alpha_views_splitk(K, E):
     close(out, C1 + (A.double().T @ B.double()).float(), rtol=5e-5)
 
 
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("M,N,K_,ta,tb", [
+    (446, 7, 256, False, False),       # H1 W2 at the Flickr shape: warp-per-row, float4 lanes
+    (446, 7, 446, False, False),       # A_hat M2: lda = 446, scalar lanes
+    (7297, 7, 256, False, True),       # tall A, B given transposed
+    (70, 7, 1433, False, False),       # K spans three shared-memory chunks, unaligned rows
+    (33, 16, 520, False, False),       # N = 16 (two outputs per lane), chunk tail of 8
+    (5, 9, 4, False, False),           # K <= 16 wins over N <= 16
+    (256, 7, 446, True, False),        # H1^T dM2: lanes over the columns of A, warps over K
+    (1433, 3, 70, True, False),
+    (500, 16, 1000, True, False),
+    (7296, 256, 7, False, True),       # dM2 W2^T: short dot products
+    (446, 49, 1, False, False),        # bias outer product
+    (3122, 257, 7, False, False),
+    (300, 1800, 16, True, True),
+])
+def test_gemm_skinny(M, N, K_, ta, tb, precision, E):
+    """Products with one dimension <= 16 (csrc/gemm.cu: skinny kernels) incl. alpha/beta and the fused epilogue; they are
+    exact-fp32 at every gemm_precision."""
+    from graphslim_b200.ops import CudaOps
+    K = CudaOps("cuda:0", precision=precision)
+    gen = torch.Generator().manual_seed(M * 13 + N * 5 + K_)
+    A = torch.randn((K_, M) if ta else (M, K_), generator=gen)
+    B = torch.randn((N, K_) if tb else (K_, N), generator=gen)
+    ref = E.gemm(A, B, ta, tb)
+    close(K.gemm(A.cuda(), B.cuda(), ta, tb), ref, rtol=2e-5)
+    C0 = torch.randn(M, N, generator=gen)
+    out = C0.clone().cuda()
+    K.gemm(A.cuda(), B.cuda(), ta, tb, out=out, alpha=0.5, beta=2.0)
+    close(out, 0.5 * ref + 2.0 * C0, rtol=2e-5)
+    bias, mask = torch.randn(N, generator=gen), torch.randn(M, N, generator=gen)
+    got = K.gemm(A.cuda(), B.cuda(), ta, tb, bias=bias.cuda(), relu=True, mask=mask.cuda())
+    close(got, torch.relu(ref + bias) * (mask > 0), rtol=2e-5)
+    # strided operands and output (views into wider buffers)
+    Aw = torch.randn(A.shape[0], A.shape[1] + 5, generator=gen)
+    Cw = torch.zeros(M, N + 3).cuda()
+    K.gemm(Aw.cuda()[:, 2:2 + A.shape[1]], B.cuda(), ta, tb, out=Cw[:, 1:1 + N])
+    close(Cw[:, 1:1 + N], E.gemm(Aw[:, 2:2 + A.shape[1]].contiguous(), B, ta, tb), rtol=2e-5)
+    assert float(Cw[:, 0].abs().max()) == 0.0 and float(Cw[:, 1 + N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N", [(500, 7), (1433, 7), (256, 16), (77, 9)])
+def test_gemm_grouped_tn_skinny(K, E, M, N):
+    gen = torch.Generator().manual_seed(M + N)
+    seg = torch.tensor([0, 64, 64, 1100, 1101, 4000], dtype=torch.int32)
+    ob = torch.tensor([3, 0, 1, 5, 4], dtype=torch.int32)
+    A = torch.randn(4000, M, generator=gen)
+    B = torch.randn(4000, N, generator=gen)
+    ref = E.gemm_grouped_tn(A, B, seg, ob, 7)
+    got = K.gemm_grouped_tn(A.cuda(), B.cuda(), seg.cuda(), ob.cuda(), 7)
+    close(got, ref, rtol=2e-5)
+    again = K.gemm_grouped_tn(A.cuda(), B.cuda(), seg.cuda(), ob.cuda(), 7)
+    assert torch.equal(got, again)                          # no atomics: bit-reproducible
+
+
 def test_gemm_grouped_tn(K, E):
     gen = torch.Generator().manual_seed(4)
     seg = torch.tensor([0, 10, 10, 300, 1000], dtype=torch.int32)

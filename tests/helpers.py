@@ -58,7 +58,9 @@ PARITY_TOL = {
     "mini_gcn_flickr": {0: (1e-2, 3e-3, 5e-3), 1: (1.5e-2, 7e-3, 6e-3)},
     "mini_sgc1_reddit_chunked": {0: (1e-5, 1e-4, 1e-5), 1: (6e-4, 2e-2, 1e-5)},
     "mini_gcondx_mse": {0: (5e-2, 1e-4, 3e-2), 1: (5e-2, 2e-3, 3e-2)},
-    "mini_doscond_gcn": {0: (2e-3, 6e-3, 2e-2), 1: (2.5e-3, 6e-3, 2.5e-2)},
+    # step 6 of this case sits on a kink: a 1e-6 relative perturbation of the dense products moves its loss by 1.7e-2
+    # (benchmarks/fixture_sensitivity_probe.py, CPU, any kernel), every other step by <= 5e-4
+    "mini_doscond_gcn": {0: (5e-2, 6e-3, 2e-2), 1: (5e-2, 6e-3, 2.5e-2)},
     "mini_doscondx_sgc2": {0: (1e-5, 1e-4, 1e-5), 1: (1e-5, 2e-3, 1e-5)},
     "mini_sgc2_cos": {0: (1e-5, 1e-4, 1e-5), 1: (1e-5, 2e-3, 1e-5)},
     "mini_sgc1_agg": {0: (1e-4, 1e-4, 1e-4), 1: (2e-3, 2e-3, 1e-3)},

@@ -88,6 +88,7 @@ SIGNATURES = {
     "gs_adam_step_table_f32": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64, c_f64, c_f64, c_vp]),
     "gs_counter_add_i32": (c_int, [c_vp, c_i32, c_vp]),
     "gs_axpby_f32": (c_int, [c_i64, c_f32, c_vp, c_f32, c_vp, c_vp]),
+    "gs_chain_run_f32": (c_int, [c_vp, c_i32, c_vp]),
     "gs_sampler_create": (c_vp, [c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "gs_sampler_destroy": (None, [c_vp]),
     "gs_sampler_set_labels": (None, [c_vp, c_vp]),

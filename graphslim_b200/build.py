@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgraphslim_b200.so")
-SOURCES = ["lib.cu", "spmm.cu", "gemm.cu", "gemm_tc.cu", "elementwise.cu", "pge.cu", "pge_fused.cu", "grouped_tn.cu", "device_sampler.cu", "host_sampler.cpp"]
+SOURCES = ["lib.cu", "spmm.cu", "gemm.cu", "gemm_tc.cu", "elementwise.cu", "pge.cu", "pge_fused.cu", "grouped_tn.cu", "chain.cu", "device_sampler.cu", "host_sampler.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-cudart", "static"]
 

@@ -44,7 +44,8 @@ class GCond(GCondBase):
         outer_loop, inner_loop = self.get_loops(args)
         # traced runs (parity tests read intermediate tensors) stay on the step-by-step path
         self.inner = InnerLoop(K, self.model, self.feat_syn, self.nnodes_syn, args.lr, outer_loop * inner_loop,
-                               use_graph=getattr(args, "cuda_graphs", True) and self.trace is None)
+                               use_graph=getattr(args, "cuda_graphs", True) and self.trace is None,
+                               use_chain=getattr(args, "inner_chain", os.environ.get("GS_INNER_CHAIN", "1") != "0"))
         self.match_graph = MatchGraph(K, self.model, self.feat_syn, args.dis_metric,
                                       use_graph=getattr(args, "cuda_graphs", True) and self.trace is None,
                                       overlap=getattr(args, "overlap_syn", os.environ.get("GS_OVERLAP_SYN", "1") != "0"))

@@ -57,7 +57,7 @@ class InnerLoop:
     path (same kernels, same order, same scalars); `use_graph=False` (or a failed capture) runs exactly that path.
     """
 
-    def __init__(self, K, model, feat_syn, n_syn, lr, steps_per_epoch, use_graph=True):
+    def __init__(self, K, model, feat_syn, n_syn, lr, steps_per_epoch, use_graph=True, use_chain=True):
         self.K, self.model, self.feat = K, model, feat_syn
         self.W = [K.zeros(*shape) for shape in model.param_shapes]
         self.m = [torch.zeros_like(w) for w in self.W]
@@ -71,6 +71,10 @@ class InnerLoop:
         self.graph = None
         self.warm = False
         self.replays = 0
+        # the whole step as ONE persistent kernel (graphslim_b200/chain.py, csrc/chain.cu) instead of a graph of ~35
+        # launches; exact-fp32 products.  Not with a fixed identity adjacency (its propagation is a torch copy).
+        self.use_chain = bool(use_chain) and self.use_graph and not getattr(model, "identity_adj", False)
+        self.chain = None
 
     def begin_epoch(self, W_host):
         """model.initialize() + a fresh Adam: new weights into the fixed buffers, optimiser state cleared."""
@@ -98,6 +102,10 @@ class InnerLoop:
         if self.steps_done >= self.capacity:
             raise RuntimeError("InnerLoop: more steps than the Adam table was sized for")
         self.steps_done += 1
+        if self.chain is not None:
+            self.chain.run()
+            self.replays += 1
+            return
         if self.graph is not None:
             self.graph.replay()
             self.replays += 1
@@ -106,6 +114,15 @@ class InnerLoop:
             self._one_step()               # first step runs eagerly: lazily configured kernels, workspace growth
             self.warm = True
             return
+        if self.use_chain:
+            from .. import chain as _chain
+            try:
+                self.chain = _chain.record(self.K, [self, self.model], self._one_step)
+                self.chain.run()
+                self.replays += 1
+                return
+            except Exception as exc:       # a call the recorder does not know, no cooperative launch: CUDA-graph path
+                self.use_chain, self.chain, self.chain_error = False, None, repr(exc)
         graph = torch.cuda.CUDAGraph()
         try:
             _capture(self.K, graph, self._one_step)

@@ -316,6 +316,27 @@ int gs_adam_table_f32(int32_t steps, double lr, double beta1, double beta2, floa
 int gs_adam_step_table_f32(int64_t n, float* p, const float* g, float* m, float* v, const float* table,
                            const int32_t* step_dev, double beta1, double beta2, double eps, void* stream);
 int gs_counter_add_i32(int32_t* counter, int32_t inc, void* stream);
+/* A recorded list of small dense operations executed by ONE persistent cooperative kernel (csrc/chain.cu): the
+ * condense-model training step of the inner loop (graphslim/condensation/gcond.py:63-72 -- model.forward, F.nll_loss,
+ * loss.backward, optimizer_model.step: ~35 dependent launches of 3-20 us each on at most N' rows) becomes one launch.
+ * `ops_dev` is a device array; the kernel walks it in order with a grid barrier before every operation whose
+ * `sync_before` is set (the recorder clears it when an operation touches nothing the operations since the last barrier
+ * wrote or read-then-overwrite).  Exact fp32 FMA, fixed summation orders (bit-reproducible).  kinds:
+ *   0 GEMM              C = epi(alpha op(A) op(B) + beta C)  (M,N,K, ta,tb, lda,ldb,ldc; bias[N], relu, mask[M x N] ldmask)
+ *   1 SOFTMAX_RESIDUAL  A = Z (M rows x N classes, lda), B = int32 labels, bias = row scale or 0, C = S or 0, p5 = R
+ *   2 COLSUM            C[N] = column sums of A (M x N, lda)
+ *   3 ADAM_TABLE        gs_adam_step_table_f32: C = p, A = g, p5 = m, p6 = v, B = table, p7 = step counter, lda = n,
+ *                       alpha = 1-beta1, beta = beta2, f0 = 1-beta2, f1 = eps
+ *   4 COUNTER_ADD       *(int32*)C += M
+ *   5 FILL              C[0..lda) = alpha */
+typedef struct gs_chain_op {
+  int32_t kind, ta, tb, relu;
+  int32_t M, N, K, sync_before;
+  int64_t lda, ldb, ldc, ldmask;
+  float alpha, beta, f0, f1;
+  uint64_t A, B, C, bias, mask, p5, p6, p7;   /* device addresses */
+} gs_chain_op;
+int gs_chain_run_f32(const gs_chain_op* ops_dev, int32_t n_ops, void* stream);
 /* y = a*x + b*y */
 int gs_axpby_f32(int64_t n, float a, const float* x, float b, float* y, void* stream);
 

@@ -76,7 +76,7 @@ def test_inner_loop_cuda_graph_matches_stepwise(name):
         # yardstick (the TMA-fed grouped kernel combines CTAs with float atomics; Adam amplifies that last-bit noise to
         # ~1e-2 of the adjacency within two epochs, graph or no graph -- benchmarks/graph_vs_step_probe.py)
         args = helpers.case_args(name, device="cuda", save_init=False, progress=False, gemm_precision=1,
-                                 cuda_graphs=graphs, grouped_mn=False)
+                                 cuda_graphs=graphs, grouped_mn=False, inner_chain=False)
         args.epochs = 2
         raw = helpers.case_graph(name)
         helpers.seed_everything(args.seed)

@@ -45,7 +45,7 @@ class GCond(GCondBase):
         # traced runs (parity tests read intermediate tensors) stay on the step-by-step path
         self.inner = InnerLoop(K, self.model, self.feat_syn, self.nnodes_syn, args.lr, outer_loop * inner_loop,
                                use_graph=getattr(args, "cuda_graphs", True) and self.trace is None,
-                               use_chain=getattr(args, "inner_chain", os.environ.get("GS_INNER_CHAIN", "1") != "0"))
+                               use_chain=getattr(args, "inner_chain", os.environ.get("GS_INNER_CHAIN", "0") == "1"))
         self.match_graph = MatchGraph(K, self.model, self.feat_syn, args.dis_metric,
                                       use_graph=getattr(args, "cuda_graphs", True) and self.trace is None,
                                       overlap=getattr(args, "overlap_syn", os.environ.get("GS_OVERLAP_SYN", "1") != "0"))

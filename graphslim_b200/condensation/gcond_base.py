@@ -57,7 +57,7 @@ class InnerLoop:
     path (same kernels, same order, same scalars); `use_graph=False` (or a failed capture) runs exactly that path.
     """
 
-    def __init__(self, K, model, feat_syn, n_syn, lr, steps_per_epoch, use_graph=True, use_chain=True):
+    def __init__(self, K, model, feat_syn, n_syn, lr, steps_per_epoch, use_graph=True, use_chain=False):
         self.K, self.model, self.feat = K, model, feat_syn
         self.W = [K.zeros(*shape) for shape in model.param_shapes]
         self.m = [torch.zeros_like(w) for w in self.W]
@@ -71,8 +71,11 @@ class InnerLoop:
         self.graph = None
         self.warm = False
         self.replays = 0
-        # the whole step as ONE persistent kernel (graphslim_b200/chain.py, csrc/chain.cu) instead of a graph of ~35
-        # launches; exact-fp32 products.  Not with a fixed identity adjacency (its propagation is a torch copy).
+        # opt-in (args.inner_chain / GS_INNER_CHAIN=1): the whole step as ONE persistent kernel (graphslim_b200/chain.py,
+        # csrc/chain.cu) instead of a graph of ~35 launches; exact-fp32 products.  Correct (tests/test_chain_gpu.py) but
+        # measured SLOWER than the graph replay -- 0.30 vs 0.18 ms per step at the arxiv shape, 130 vs 77 us at Cora: with
+        # one 32 x 32 tile per CTA the small-N products occupy a fifth of the SMs and each operation pays two dependent
+        # L2 round trips plus a grid barrier.  Not with a fixed identity adjacency.
         self.use_chain = bool(use_chain) and self.use_graph and not getattr(model, "identity_adj", False)
         self.chain = None
 

@@ -12,7 +12,7 @@
 #   launches:<workload>     ncu launch list (gpu__time_duration) of a short bench run
 #   pge[:quick][:ncu]       fused PGE kernels: accuracy / timing (benchmarks/pge_fused_check.py), optional ncu --set full
 #   spmm[:ncu]              standalone SpMM sweep (benchmarks/spmm_sweep.py)
-#   mtests:<N>              torchrun -m pytest of the NCCL tests on N GPUs
+#   mtests:<N>              the NCCL tests (they spawn one worker per GPU themselves) on a box with N GPUs
 TAG=${GS_TAG:-r2}
 mkdir -p gpurun_out
 for cmd in "$@"; do
@@ -59,9 +59,10 @@ PY
       ( time timeout 1200 python benchmarks/spmm_sweep.py --out gpurun_out/${TAG}_spmm_sweep.json ${GS_SPMM_FLAGS} ) > gpurun_out/${TAG}_spmm_sweep.log 2>&1
       tail -30 gpurun_out/${TAG}_spmm_sweep.log | cut -c1-250 ;;
     mtests)
+      # the NCCL tests spawn their own one-process-per-GPU workers (torch.multiprocessing): plain pytest on a box with
+      # >= 2 GPUs.  (Under torchrun every rank would spawn its own group on the same GPUs and the groups deadlock.)
       log=gpurun_out/${TAG}_pytest_nccl_${a}.log
-      ( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $a --master-addr 127.0.0.1 --master-port 29515 \
-          -m pytest tests -q -m gpu -k "nccl or sharded or row_partition" -x ) > $log 2>&1; echo "rc=$?" >> $log
+      ( time timeout 420 python -m pytest tests -q -m gpu -k "nccl or sharded or row_partition" -x ) > $log 2>&1; echo "rc=$?" >> $log
       tail -8 $log | cut -c1-300 ;;
     *) echo "unknown sub-command $cmd" ;;
   esac

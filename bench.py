@@ -422,8 +422,10 @@ def run_ours(ns):
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0.record()
+    hw0 = time.perf_counter()
     for it in range(W_, W_ + K_):
         agent.run_epoch(it)
+    host_issue_ms = (time.perf_counter() - hw0) * 1e3 / K_       # host time to ISSUE an epoch (no sync inside)
     t1.record()
     torch.cuda.synchronize()
     kernel_times = agent.K.stop_timing()
@@ -581,6 +583,9 @@ def run_ours(ns):
         # and the host time the main thread spent waiting for the sampler worker
         "phases": {k[6:]: round(v[1] / ms, 4) for k, v in sorted(kernel_times.items()) if k.startswith("phase_")},
         "host_wait_sampler_frac": round(host_wait_sampler * 1e3 / ms, 4),
+        # host time the main thread needs to issue one epoch (nothing in the epoch synchronises): close to ms_per_step
+        # means the launch rate, not the device, bounds the step
+        "host_issue_ms_per_step": round(host_issue_ms, 3),
         "sampler_ms_per_outer_step": sampler_stats,
     }
     print(json.dumps(line))

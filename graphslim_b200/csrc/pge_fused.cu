@@ -821,6 +821,14 @@ pge_l2_bwd_dx_kernel(const __grid_constant__ CUtensorMap map_y2, BwdParams p) {
       };
       const int et = q * 32 + lane;           // epilogue thread id 0..127
       for (int idx = et; idx < BJ * H; idx += kEpiThreads) ga_sm[idx] = 0.f;
+      // BatchNorm constants of this lane's column of every 32-column block: tile independent, loaded once
+      float grs_c[C::NB], off_c[C::NB];
+#pragma unroll
+      for (int b = 0; b < C::NB; ++b) {
+        const int c = b * 32 + lane;
+        grs_c[b] = __ldg(p.bn1.gamma + c) * __ldg(p.bn1.rstd + c);
+        off_c[b] = fmaf(-__ldg(p.bn1.mean + c), grs_c[b], __ldg(p.bn1.beta + c));
+      }
       named_bar_sync(1, kEpiThreads);
       for (int t = t0; t < t1; ++t, ++tcount) {
         const int ib = t / p.g.tiles_j, jb = t - ib * p.g.tiles_j;
@@ -831,6 +839,16 @@ pge_l2_bwd_dx_kernel(const __grid_constant__ CUtensorMap map_y2, BwdParams p) {
         const float* pa_base = p.Pa + (int64_t)(jb * BJ) * H + lane;
         const float* pb_base = p.Pb + (int64_t)(p.g.i_first + ib * BI + 4 * q) * H + lane;
         const int nj = min(BJ, p.g.n - jb * BJ), ni = min(4, p.g.n_i - (ib * BI + 4 * q));   // valid rows (ni may be <= 0)
+        // the 8 Pa and 4 Pb values of a block are requested one block ahead (they were the exposed latency of this role:
+        // ncu showed the fused-reduction kernel 180 us behind the variant that only stores dH1)
+        float pa_n[BJ], pb_n[4];
+        auto fetch = [&](int c) {
+#pragma unroll
+          for (int jj = 0; jj < BJ; ++jj) pa_n[jj] = __ldg(pa_base + (int64_t)(jj < nj ? jj : 0) * H + c);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pb_n[k] = (ni > 0) ? __ldg(pb_base + (int64_t)(k < ni ? k : 0) * H + c) : 0.f;
+        };
+        fetch(0);
         const int acc = tcount & 1;
         mbar_wait(smem_u32(&bars.tfull[acc]), (tcount >> 1) & 1);
         tc_fence_after();
@@ -839,13 +857,13 @@ pge_l2_bwd_dx_kernel(const __grid_constant__ CUtensorMap map_y2, BwdParams p) {
           const int c = b * 32;
           float pa[BJ], pb[4];
 #pragma unroll
-          for (int jj = 0; jj < BJ; ++jj) pa[jj] = __ldg(pa_base + (int64_t)(jj < nj ? jj : 0) * H + c);
+          for (int jj = 0; jj < BJ; ++jj) pa[jj] = pa_n[jj];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) pb[k] = (ni > 0) ? __ldg(pb_base + (int64_t)(k < ni ? k : 0) * H + c) : 0.f;
-          const float grs = __ldg(p.bn1.gamma + c + lane) * __ldg(p.bn1.rstd + c + lane);
-          const float off = fmaf(-__ldg(p.bn1.mean + c + lane), grs, __ldg(p.bn1.beta + c + lane));
+          for (int k = 0; k < 4; ++k) pb[k] = pb_n[k];
+          const float grs = grs_c[b], off = off_c[b];
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + c), r);
+          if (b + 1 < C::NB) fetch(c + 32);
           tmem_ld_wait();
           stage_block(st, lane, r);
           __syncwarp();

@@ -48,7 +48,8 @@ class GCond(GCondBase):
                                use_chain=getattr(args, "inner_chain", os.environ.get("GS_INNER_CHAIN", "0") == "1"))
         self.match_graph = MatchGraph(K, self.model, self.feat_syn, args.dis_metric,
                                       use_graph=getattr(args, "cuda_graphs", True) and self.trace is None,
-                                      overlap=getattr(args, "overlap_syn", os.environ.get("GS_OVERLAP_SYN", "1") != "0"))
+                                      overlap=getattr(args, "overlap_syn", os.environ.get("GS_OVERLAP_SYN", "1") != "0"),
+                                      adj_buffer=None if self.x_variant else self.inner.adj)
         self.loss_avg, self.best_val = 0, 0
         self.adj_syn_inner = None
         self._pge_ready = None
@@ -125,7 +126,8 @@ class GCond(GCondBase):
             else:
                 with K.timed("phase_pge_inference"):
                     self.adj_syn_inner = pge.inference(self.feat_syn, keep=True)
-                    adj_inner, r_inner = K.dense_gcn_norm(self.adj_syn_inner)
+                    # normalised straight into the inner loop's fixed adjacency buffer (also the matching graphs' input)
+                    adj_inner, r_inner = K.dense_gcn_norm(self.adj_syn_inner, out=self.inner.adj)
                     self._pge_ready = (adj_inner, r_inner)
             with K.timed("phase_inner_loop"):
                 self.inner.set_adj(adj_inner)

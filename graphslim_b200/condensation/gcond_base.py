@@ -169,8 +169,11 @@ class MatchGraph:
     configuration, workspace growth), second call captures, later calls replay; a failed capture falls back to the
     step-by-step path for good."""
 
-    def __init__(self, K, model, feat_syn, metric, use_graph=True, overlap=True):
+    def __init__(self, K, model, feat_syn, metric, use_graph=True, overlap=True, adj_buffer=None):
         self.K, self.model, self.feat, self.metric = K, model, feat_syn, metric
+        # adj_buffer: a fixed tensor the caller normally passes as `adj` (the inner loop's adjacency buffer, which the
+        # PGE inference writes in place): captured by address, so the steady-state step copies nothing in
+        self.adj_buffer = adj_buffer
         self.use_graph = bool(use_graph) and torch.device(K.device).type == "cuda"
         self.overlap = bool(overlap)
         self.graph, self.graph_fwd, self.calls, self.replays = None, None, 0, 0
@@ -214,7 +217,12 @@ class MatchGraph:
             return self._body(gr, adj, need_dA)
         if self.graph is None:
             self.gr = [g.clone() for g in gr]
-            self.adj = adj.clone()
+            if self.adj_buffer is not None and self.adj_buffer.shape == adj.shape:
+                self.adj = self.adj_buffer
+                if adj.data_ptr() != self.adj.data_ptr():
+                    self.adj.copy_(adj)
+            else:
+                self.adj = adj.clone()
             g_fwd, g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             ws_main = getattr(K, "_ws", None)
             try:
@@ -233,7 +241,8 @@ class MatchGraph:
             self.side = torch.cuda.Stream(K.device)
         else:
             for dst, src in zip(self.gr, gr):
-                dst.copy_(src)
+                if src.data_ptr() != dst.data_ptr():       # real_grads(out=...) already wrote into the fixed buffers
+                    dst.copy_(src)
         if started:
             torch.cuda.current_stream(K.device).wait_stream(self.side)
         else:
@@ -241,6 +250,10 @@ class MatchGraph:
         self.graph.replay()
         self.replays += 1
         return self.out
+
+    def real_out(self):
+        """The fixed real-side gradient buffers once the graphs exist (hand them to model.real_grads(out=...))."""
+        return self.gr if (self.use_graph and self.graph is not None) else None
 
     def run(self, gr, adj, need_dA):
         self.start(adj, need_dA)
@@ -439,7 +452,8 @@ class GCondBase:
         if self.trace:
             self.trace("sample", rb=rb)
         with K.timed("phase_real_grads"):
-            gr = model.real_grads(rb, self.features, self.ones_full, self.features_padded)
+            gr = model.real_grads(rb, self.features, self.ones_full, self.features_padded,
+                                  out=mg.real_out() if use_mg else None)
         if use_mg:
             with K.timed("phase_syn_graph"):                 # (forward + gradients) | matching + backward: two replays
                 loss, dX, dA = mg.finish(gr)

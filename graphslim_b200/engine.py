@@ -84,9 +84,12 @@ class SGC1(_ModelBase):
     is_bias = [False, True]
 
     # ---- real side: H^r = A1 (A2 X[n_id]) does not depend on W, so propagate at feature width once
-    def real_grads(self, rb, X_full, ones_full, X_padded=None):
+    def real_grads(self, rb, X_full, ones_full, X_padded=None, out=None):
+        """`out`: optional list of fixed result buffers (one per parameter, class-column layout), cleared and written in
+        place of fresh allocations (the matching graph's input buffers)."""
         K = self.K
         W, b = self.W
+        o = out if out is not None else [None] * 2
         d = X_full.shape[1]
         Xp = X_full if X_padded is None else X_padded      # rows padded with zeros to a float4 multiple
         T = K.spmm(rb.blocks_fwd[0].with_global_cols(), Xp)
@@ -98,8 +101,8 @@ class SGC1(_ModelBase):
         Z = K.gemm(T, W)
         K.gemm(t, b.view(1, -1), out=Z, beta=1.0)
         _, R = K.softmax_residual(Z, rb.labels, rb.inv_b)
-        gW = K.gemm_grouped_tn(T, R, rb.seg[0], rb.out_block, self.lay.nblk, aligned=rb.aligned)
-        gb = K.gemm_grouped_tn(t, R, rb.seg[0], rb.out_block, self.lay.nblk, aligned=rb.aligned)
+        gW = K.gemm_grouped_tn(T, R, rb.seg[0], rb.out_block, self.lay.nblk, aligned=rb.aligned, out=o[0])
+        gb = K.gemm_grouped_tn(t, R, rb.seg[0], rb.out_block, self.lay.nblk, aligned=rb.aligned, out=o[1])
         return [gW, gb]
 
     def syn_forward(self, X, A):
@@ -162,9 +165,10 @@ class SGC2(_ModelBase):
     widths = property(lambda s: [s.h, s.h, s.C, s.C])
     is_bias = [False, True, False, True]
 
-    def real_grads(self, rb, X_full, ones_full, X_padded=None):
+    def real_grads(self, rb, X_full, ones_full, X_padded=None, out=None):
         K = self.K
         W1, b1, W2, b2 = self.W
+        o = out if out is not None else [None] * 4
         Xg = K.gather_rows(X_full, rb.nid)
         H1 = K.gemm(Xg, W1, bias=b1, relu=True)
         U = K.gemm(H1, W2, bias=b2)
@@ -176,15 +180,15 @@ class SGC2(_ModelBase):
         for blk in reversed(rb.blocks_fwd):
             dU = K.spmm(blk.csr_t, dU)
         seg, ids, nb = rb.seg[-1], rb.out_block, self.lay.nblk
-        gW2 = K.gemm_grouped_tn(H1, dU, seg, ids, nb, aligned=rb.aligned)
-        gb2 = K.segment_colsum(dU, seg, ids, nb)
+        gW2 = K.gemm_grouped_tn(H1, dU, seg, ids, nb, aligned=rb.aligned, out=o[2])
+        gb2 = K.segment_colsum(dU, seg, ids, nb, out=o[3])
         if K.mlp_bwd_grouped_supported(Xg, H1, dU, rb.aligned):
             # dA1 = (dU W2^T) . [H1 > 0] generated inside the grouped product: never written to / re-read from HBM
-            gW1, gb1 = K.mlp_bwd_grouped(Xg, H1, dU, W2, seg, ids, nb)
+            gW1, gb1 = K.mlp_bwd_grouped(Xg, H1, dU, W2, seg, ids, nb, out=None if out is None else (o[0], o[1]))
         else:
             dA1 = K.gemm(dU, W2, tb=True, mask=H1)
-            gW1 = K.gemm_grouped_tn(Xg, dA1, seg, ids, nb, aligned=rb.aligned)
-            gb1 = K.segment_colsum(dA1, seg, ids, nb)
+            gW1 = K.gemm_grouped_tn(Xg, dA1, seg, ids, nb, aligned=rb.aligned, out=o[0])
+            gb1 = K.segment_colsum(dA1, seg, ids, nb, out=o[1])
         return [gW1, gb1, gW2, gb2]
 
     def syn_forward(self, X, A):
@@ -276,9 +280,10 @@ class GCN2(_ModelBase):
     widths = property(lambda s: [s.h, s.h, s.C, s.C])
     is_bias = [False, True, False, True]
 
-    def real_grads(self, rb, X_full, ones_full, X_padded=None):
+    def real_grads(self, rb, X_full, ones_full, X_padded=None, out=None):
         K = self.K
         W1, b1, W2, b2 = self.W
+        o = out if out is not None else [None] * 4
         outer, inner = rb.blocks_fwd
         Xp = X_full if X_padded is None else X_padded
         T2 = K.spmm(outer.with_global_cols(), Xp)[:, :X_full.shape[1]]   # (A2 X[n_id]) W1 == A2 (X[n_id] W1)
@@ -287,16 +292,16 @@ class GCN2(_ModelBase):
         Z = K.bias_act(K.spmm(inner.csr, M2), b2, relu=False)
         _, R = K.softmax_residual(Z, rb.labels, rb.inv_b)
         ids, nb = rb.out_block, self.lay.nblk
-        gb2 = K.segment_colsum(R, rb.seg[0], ids, nb)
+        gb2 = K.segment_colsum(R, rb.seg[0], ids, nb, out=o[3])
         dM2 = K.spmm(inner.csr_t, R)
         seg1 = rb.seg[1]
-        gW2 = K.gemm_grouped_tn(H1, dM2, seg1, ids, nb, aligned=rb.aligned)
+        gW2 = K.gemm_grouped_tn(H1, dM2, seg1, ids, nb, aligned=rb.aligned, out=o[2])
         if K.mlp_bwd_grouped_supported(T2, H1, dM2, rb.aligned):
-            gW1, gb1 = K.mlp_bwd_grouped(T2, H1, dM2, W2, seg1, ids, nb)
+            gW1, gb1 = K.mlp_bwd_grouped(T2, H1, dM2, W2, seg1, ids, nb, out=None if out is None else (o[0], o[1]))
         else:
             dA1 = K.gemm(dM2, W2, tb=True, mask=H1)
-            gb1 = K.segment_colsum(dA1, seg1, ids, nb)
-            gW1 = K.gemm_grouped_tn(T2, dA1, seg1, ids, nb, aligned=rb.aligned)
+            gb1 = K.segment_colsum(dA1, seg1, ids, nb, out=o[1])
+            gW1 = K.gemm_grouped_tn(T2, dA1, seg1, ids, nb, aligned=rb.aligned, out=o[0])
         return [gW1, gb1, gW2, gb2]
 
     def syn_forward(self, X, A):

@@ -184,7 +184,16 @@ class CudaOps:
             self._ws = ws
         return ws
 
-    def gemm_grouped_tn(self, A, B, seg, out_block, nblk, aligned=False, precision=None):
+    def _zeroed(self, out, rows, cols):
+        """A zeroed (rows x cols) result: fresh, or the caller's fixed buffer cleared in place (the matching graph's input
+        buffers: writing there directly saves a device-to-device copy and an allocation per gradient and step)."""
+        if out is None:
+            return self.zeros(rows, cols)
+        if out.shape != (rows, cols) or not out.is_contiguous() or out.dtype is not torch.float32:
+            raise ValueError(f"out must be a contiguous float32 ({rows} x {cols}) tensor, got {tuple(out.shape)}")
+        return out.zero_()
+
+    def gemm_grouped_tn(self, A, B, seg, out_block, nblk, aligned=False, precision=None, out=None):
         """out[:, out_block[g]*N:(out_block[g]+1)*N] = A[seg[g]:seg[g+1]]^T @ B[seg[g]:seg[g+1]]; other blocks zero.
         aligned=True promises 64-row-aligned segments (the sampler's padding), which lets the product run on tcgen05."""
         lda, ldb = _mat(A, "A"), _mat(B, "B")
@@ -193,7 +202,7 @@ class CudaOps:
         prec = (self.precision if precision is None else precision) if aligned else 0
         if prec and self._mn_ok(A, lda, B, ldb, M, N, prec):
             # both operands consumed row-major through TMA as MN-major UMMA operands (csrc/grouped_tn.cu)
-            out = self.zeros(M, nblk * N)
+            out = self._zeroed(out, M, nblk * N)
             _lib.check(self.lib.gs_gemm_grouped_mn_f32(G, _ptr(seg), _ptr(out_block), M, N, Kt, _ptr(A), lda, _ptr(B),
                                                        ldb, _ptr(out), nblk * N, prec, self.stream),
                        "gs_gemm_grouped_mn_f32")
@@ -203,7 +212,10 @@ class CudaOps:
             ws_bytes = int(self.lib.gs_gemm_workspace_bytes(M, N, Kt, prec))
             if ws_bytes:
                 ws = self._gemm_workspace(ws_bytes)
-        out = self.zeros(M, nblk * N) if (G < nblk or prec) else self.empty(M, nblk * N)
+        if out is not None or G < nblk or prec:
+            out = self._zeroed(out, M, nblk * N)
+        else:
+            out = self.empty(M, nblk * N)
         _lib.check(self.lib.gs_gemm_grouped_tn_f32(G, _ptr(seg), _ptr(out_block), M, N, Kt, _ptr(A), lda, _ptr(B), ldb,
                                                    _ptr(out), nblk * N, prec, _ptr(ws), ws_bytes, self.stream),
                    "gs_gemm_grouped_tn_f32")
@@ -220,24 +232,25 @@ class CudaOps:
                 and H1.shape[1] == 256 and dU.shape[1] % 4 == 0 and 4 <= dU.shape[1] <= 64
                 and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (X, H1, dU)))
 
-    def mlp_bwd_grouped(self, X, H1, dU, W2, seg, out_block, nblk):
+    def mlp_bwd_grouped(self, X, H1, dU, W2, seg, out_block, nblk, out=None):
         """(gW1, gb1) of the hidden layer on the real side for all classes: dA1 = (dU W2^T) . [H1 > 0] is generated on
         chip, gW1 block g = X[rows g]^T dA1[rows g], gb1 block g = column sums of dA1[rows g]  (csrc/grouped_tn.cu)."""
         ldx, ldh, ldu, ldw = _mat(X, "X"), _mat(H1, "H1"), _mat(dU, "dU"), _mat(W2, "W2")
         M, N, Cw, Kt = X.shape[1], H1.shape[1], dU.shape[1], X.shape[0]
         G = seg.numel() - 1
-        gW1, gb1 = self.zeros(M, nblk * N), self.zeros(1, nblk * N)
+        gW1 = self._zeroed(None if out is None else out[0], M, nblk * N)
+        gb1 = self._zeroed(None if out is None else out[1], 1, nblk * N)
         _lib.check(self.lib.gs_mlp_bwd_grouped_f32(G, _ptr(seg), _ptr(out_block), M, N, Cw, Kt, _ptr(X), ldx, _ptr(H1),
                                                    ldh, _ptr(dU), ldu, _ptr(W2), ldw, _ptr(gW1), nblk * N, _ptr(gb1),
                                                    self.precision, self.stream), "gs_mlp_bwd_grouped_f32")
         return gW1, gb1
 
-    def segment_colsum(self, X, seg, out_block, nblk):
+    def segment_colsum(self, X, seg, out_block, nblk, out=None):
         """(1 x nblk*cols): block out_block[g] holds the column sums of rows seg[g]..seg[g+1] of X; other blocks zero."""
         ldx = _mat(X, "X")
         cols = X.shape[1]
         G = seg.numel() - 1
-        out = self.zeros(1, nblk * cols)
+        out = self._zeroed(out, 1, nblk * cols)
         _lib.check(self.lib.gs_segment_colsum_f32(G, _ptr(seg), _ptr(out_block), cols, _ptr(X), ldx, X.shape[0],
                                                   _ptr(out), self.stream), "gs_segment_colsum_f32")
         return out
@@ -428,9 +441,11 @@ class CudaOps:
         return out
 
     # -- dense normalisation ---------------------------------------------------------------------
-    def dense_gcn_norm(self, A):
+    def dense_gcn_norm(self, A, out=None):
         n = A.shape[0]
-        Ahat, r = self.empty(n, n), self.empty(n)
+        Ahat, r = (self.empty(n, n) if out is None else out), self.empty(n)
+        if Ahat.shape != (n, n) or not Ahat.is_contiguous():
+            raise ValueError("dense_gcn_norm: out must be a contiguous (n x n) tensor")
         _lib.check(self.lib.gs_dense_gcn_norm_fwd_f32(n, _ptr(A), _ptr(Ahat), _ptr(r), self.stream),
                    "gs_dense_gcn_norm_fwd_f32")
         return Ahat, r

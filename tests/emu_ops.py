@@ -51,9 +51,9 @@ class EmuOps:
         out.copy_(r)
         return out
 
-    def gemm_grouped_tn(self, A, B, seg, out_block, nblk, aligned=False, precision=None):
+    def gemm_grouped_tn(self, A, B, seg, out_block, nblk, aligned=False, precision=None, out=None):
         M, N = A.shape[1], B.shape[1]
-        out = torch.zeros(M, nblk * N, device=self.device)
+        out = torch.zeros(M, nblk * N, device=self.device) if out is None else out.zero_()
         seg = seg.tolist()
         for g, ob in enumerate(out_block.tolist()):
             r0, r1 = seg[g], seg[g + 1]
@@ -63,13 +63,15 @@ class EmuOps:
     def mlp_bwd_grouped_supported(self, X, H1, dU, aligned):
         return bool(getattr(self, "fuse_mlp_bwd", True))
 
-    def mlp_bwd_grouped(self, X, H1, dU, W2, seg, out_block, nblk):
+    def mlp_bwd_grouped(self, X, H1, dU, W2, seg, out_block, nblk, out=None):
         dA1 = (dU @ W2.T) * (H1 > 0)
-        return self.gemm_grouped_tn(X, dA1, seg, out_block, nblk), self.segment_colsum(dA1, seg, out_block, nblk)
+        o0, o1 = (None, None) if out is None else out
+        return (self.gemm_grouped_tn(X, dA1, seg, out_block, nblk, out=o0),
+                self.segment_colsum(dA1, seg, out_block, nblk, out=o1))
 
-    def segment_colsum(self, X, seg, out_block, nblk):
+    def segment_colsum(self, X, seg, out_block, nblk, out=None):
         cols = X.shape[1]
-        out = torch.zeros(1, nblk * cols, device=self.device)
+        out = torch.zeros(1, nblk * cols, device=self.device) if out is None else out.zero_()
         sl = seg.tolist()
         for g, ob in enumerate(out_block.tolist()):
             out[0, ob * cols:(ob + 1) * cols] = X[sl[g]:sl[g + 1]].sum(0)
@@ -196,12 +198,13 @@ class EmuOps:
         return out
 
     # ---- dense norm
-    def dense_gcn_norm(self, A):
+    def dense_gcn_norm(self, A, out=None):
         n = A.shape[0]
         mx = A + torch.eye(n, device=self.device)
         r = mx.sum(1).pow(-0.5)
         r[torch.isinf(r)] = 0.0
-        return (r[:, None] * mx) * r[None, :], r
+        res = (r[:, None] * mx) * r[None, :]
+        return (res if out is None else out.copy_(res)), r
 
     def dense_gcn_norm_bwd(self, dAhat, Ahat, r):
         rd = (dAhat * Ahat).sum(1)

@@ -254,8 +254,8 @@ constexpr int kFwdMmaWarp = 16, kFwdTmaWarp = 17;
 constexpr int kFwdThreads = 18 * 32;
 constexpr uint32_t kFwdStagingBytes = kFwdEpiWarps * 32 * 32 * 4;     // dense swizzled 32 x 32 tiles, one per warp
 
-template <int H, int NPASS>
-__global__ void __launch_bounds__(kFwdThreads, 1) pge_l2_fwd_kernel(FwdParams p) {
+template <int H, int NPASS, bool kTmaStore>
+__global__ void __launch_bounds__(kFwdThreads, 1) pge_l2_fwd_kernel(const __grid_constant__ CUtensorMap map_y2, FwdParams p) {
   using C = Cfg<H, NPASS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -368,7 +368,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) pge_l2_fwd_kernel(FwdParams p)
           *reinterpret_cast<float4*>(st + lane * 32 + ((jc ^ (lane & 7)) << 2)) =
               make_float4(__uint_as_float(r[4 * jc]), __uint_as_float(r[4 * jc + 1]), __uint_as_float(r[4 * jc + 2]),
                           __uint_as_float(r[4 * jc + 3]));
-        __syncwarp();
+        if constexpr (kTmaStore) {
+          // The tile IS the SWIZZLE_128B image of a (4 il x 8 jl x 32 columns) box of Y2 (rows of 128 bytes, 16-byte chunk
+          // ^ row & 7, 1 KB-aligned): one TMA store per block instead of 8 LDS.128 + 8 STG.128 per lane.  ncu had the LSU
+          // data pipe of this kernel at 90 % (11.9 k wavefronts per tile against 6.1 k MMA cycles); rows / columns outside
+          // the slice are clipped by the tensor map.
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_y2, smem_u32(st), b * 32, jb * BJ, ib * BI + 4 * q);
+            bulk_commit_group();
+          }
+        } else {
+          __syncwarp();
+        }
         // rows outside the slice were generated as zeros, so they add nothing to the sums
         float a1 = 0.f, a2 = 0.f;
 #pragma unroll
@@ -379,13 +392,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) pge_l2_fwd_kernel(FwdParams p)
         }
         ps1[bi] += a1;
         ps2[bi] += a2;
+        if constexpr (kTmaStore) {
+          if (lane == 0) bulk_wait_group_read0();           // the TMA engine has read the tile: it may be rewritten
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int row = rsub + 4 * k, u = q * 32 + row;
-          const int li = ib * BI + (u >> 3), j = jb * BJ + (u & 7);
-          if (li < p.g.n_i && j < p.g.n)
-            *reinterpret_cast<float4*>(p.Y2 + ((int64_t)li * p.g.n + j) * H + b * 32 + ch * 4) =
-                *reinterpret_cast<const float4*>(st + row * 32 + ((ch ^ (row & 7)) << 2));
+          for (int k = 0; k < 8; ++k) {
+            const int row = rsub + 4 * k, u = q * 32 + row;
+            const int li = ib * BI + (u >> 3), j = jb * BJ + (u & 7);
+            if (li < p.g.n_i && j < p.g.n)
+              *reinterpret_cast<float4*>(p.Y2 + ((int64_t)li * p.g.n + j) * H + b * 32 + ch * 4) =
+                  *reinterpret_cast<const float4*>(st + row * 32 + ((ch ^ (row & 7)) << 2));
+          }
         }
         __syncwarp();
       }
@@ -399,6 +416,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) pge_l2_fwd_kernel(FwdParams p)
           ps1[b] = ps2[b] = 0.f;
         }
       }
+    }
+    if constexpr (kTmaStore) {
+      if (lane == 0) bulk_wait_group0();                    // every store of this warp has landed
+      __syncwarp();
     }
     // column sums: the four lane quarters of each block parity are combined through shared memory, one double atomic
     // per column, statistic and CTA
@@ -1163,7 +1184,7 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 // Y2 slice (n_i * n rows x h fp32) as a 3-D tensor (column, j, i); a box is 32 columns x BJ j x box_i i
-static int encode_y2_map(CUtensorMap* map, const float* Y2, int h, int n, int n_i, int box_i) {
+static int encode_y2_map(CUtensorMap* map, const float* Y2, int h, int n, int n_i, int box_i, bool swizzle128 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error_msg("cuTensorMapEncodeTiled is not available from this driver");
@@ -1174,8 +1195,8 @@ static int encode_y2_map(CUtensorMap* map, const float* Y2, int h, int n, int n_
   const cuuint32_t box[3] = {32, (cuuint32_t)BJ, (cuuint32_t)box_i};
   const cuuint32_t es[3] = {1, 1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(Y2), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[96];
     std::snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -1212,10 +1233,17 @@ static int launch_fwd(FwdParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)C::kStages * C::kStageBytes + kFwdStagingBytes + 1024;
   static bool configured = false;
   if (!configured) {
-    const int rc = set_smem(pge_l2_fwd_kernel<H, NPASS>, smem, "cudaFuncSetAttribute(pge_l2_fwd)");
+    int rc = set_smem(pge_l2_fwd_kernel<H, NPASS, true>, smem, "cudaFuncSetAttribute(pge_l2_fwd)");
+    if (rc) return rc;
+    rc = set_smem(pge_l2_fwd_kernel<H, NPASS, false>, smem, "cudaFuncSetAttribute(pge_l2_fwd)");
     if (rc) return rc;
     configured = true;
   }
+  // GS_PGE_TMA_STORE=0: the epilogue stores Y2 with per-lane float4 stores instead of one TMA store per block
+  static const int tma_store = [] {
+    const char* e = getenv("GS_PGE_TMA_STORE");
+    return e ? atoi(e) : 1;
+  }();
   static const int two_cta = [] {
     const char* e = getenv("GS_PGE_2CTA");
     return e ? atoi(e) : 0;
@@ -1232,7 +1260,11 @@ static int launch_fwd(FwdParams& p, cudaStream_t st) {
     return finish_launch("pge_l2_fwd2");
   }
   const int grid = p.g.num_tiles < kNumSMs ? p.g.num_tiles : kNumSMs;
-  pge_l2_fwd_kernel<H, NPASS><<<grid, kFwdThreads, smem, st>>>(p);
+  CUtensorMap map;
+  const int rc = encode_y2_map(&map, p.Y2, H, p.g.n, p.g.n_i, 4, true);   // box: 32 columns x 8 j x 4 i, SWIZZLE_128B
+  if (rc) return rc;
+  if (tma_store) pge_l2_fwd_kernel<H, NPASS, true><<<grid, kFwdThreads, smem, st>>>(map, p);
+  else pge_l2_fwd_kernel<H, NPASS, false><<<grid, kFwdThreads, smem, st>>>(map, p);
   return finish_launch("pge_l2_fwd");
 }
 

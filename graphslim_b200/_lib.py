@@ -89,6 +89,7 @@ SIGNATURES = {
     "gs_counter_add_i32": (c_int, [c_vp, c_i32, c_vp]),
     "gs_axpby_f32": (c_int, [c_i64, c_f32, c_vp, c_f32, c_vp, c_vp]),
     "gs_chain_run_f32": (c_int, [c_vp, c_i32, c_vp]),
+    "gs_np_legacy_class_batches": (c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "gs_sampler_create": (c_vp, [c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "gs_sampler_destroy": (None, [c_vp]),
     "gs_sampler_set_labels": (None, [c_vp, c_vp]),

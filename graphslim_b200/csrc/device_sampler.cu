@@ -85,7 +85,7 @@ __device__ __forceinline__ uint32_t mt_tw(uint32_t u, uint32_t v) {
 }
 
 // R[0] <- current state; R[b] <- regeneration of R[b-1].  One CTA; the three phases of a block only depend on the
-// previous phase (new[i] = new[i-227] ^ tw(old[i], old[i+1]) for i >= 227), so a block costs four barriers.
+// previous phase (new[i] = new[i-227] ^ tw(old[i], old[i+1]) for i >= 227), so a block costs three barriers.
 __global__ void __launch_bounds__(256) mt_generate_kernel(const MtDev* __restrict__ mt, uint32_t* __restrict__ R,
                                                           int nblocks, int64_t* __restrict__ step_info) {
   __shared__ uint32_t cur[2][624];
@@ -122,9 +122,8 @@ __global__ void __launch_bounds__(256) mt_generate_kernel(const MtDev* __restric
       const uint32_t v = nw[i - 227] ^ mt_tw(o[i], o[i + 1]);
       nw[i] = v;
       dst[i] = v;
-    }
-    __syncthreads();
-    if (tid == 0) {
+    } else if (tid == 169) {
+      // the last word needs nw[396] (second phase) and nw[0] (first phase): it rides along with the third phase
       const uint32_t v = nw[396] ^ mt_tw(o[623], nw[0]);
       nw[623] = v;
       dst[623] = v;

@@ -526,4 +526,100 @@ int64_t gs_sampler_sample_step(gs_sampler* S, int32_t n_class, const int64_t* ba
   return gs_sampler_finish_step(S, J, out, out_cap, desc);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Class batches: `np.random.permutation(members_of_class)[:batch]` for every class in order
+// (graphslim/dataset/loader.py:222, numpy's GLOBAL legacy generator).  numpy's legacy RandomState.permutation of a 1-D
+// array copies it and runs `_shuffle_raw`: for i = n-1 .. 1: j = random_interval(i); swap(x[i], x[j]), where
+// random_interval(max) masks 32-bit MT19937 outputs with the smallest 2^k - 1 >= max and rejects values > max (64-bit
+// outputs only for max > 0xffffffff, which cannot occur here).  The stream is frozen ("legacy"), so restating it keeps
+// the index selection bit-exact -- and takes the shuffles (154 k elements per outer step at the Reddit shape, 2 ms in
+// numpy on the box's host) off the interpreter lock: the call runs without the GIL next to the thread that issues the
+// kernels.  `key` (624 words) and `pos` are np.random.get_state()[1:3], updated in place for np.random.set_state().
+static inline void np_mt19937_gen(uint32_t* mt) {
+  constexpr int N = 624, M = 397;
+  constexpr uint32_t MATRIX_A = 0x9908b0dfu, UPPER = 0x80000000u, LOWER = 0x7fffffffu;
+  int i = 0;
+  uint32_t y;
+  for (; i < N - M; ++i) {
+    y = (mt[i] & UPPER) | (mt[i + 1] & LOWER);
+    mt[i] = mt[i + M] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+  }
+  for (; i < N - 1; ++i) {
+    y = (mt[i] & UPPER) | (mt[i + 1] & LOWER);
+    mt[i] = mt[i + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+  }
+  y = (mt[N - 1] & UPPER) | (mt[0] & LOWER);
+  mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+}
+
+// tempered outputs of the current state block, consumed sequentially (the tempering vectorises; a draw is then a load)
+struct NpStream {
+  uint32_t* mt;
+  uint32_t out[624];
+  int pos;
+  static inline uint32_t temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+  NpStream(uint32_t* key, int p) : mt(key), pos(p) {
+    for (int i = 0; i < 624; ++i) out[i] = temper(mt[i]);
+  }
+  inline uint32_t next32() {
+    if (pos >= 624) {
+      np_mt19937_gen(mt);
+      for (int i = 0; i < 624; ++i) out[i] = temper(mt[i]);
+      pos = 0;
+    }
+    return out[pos++];
+  }
+};
+
+int gs_np_legacy_class_batches(uint32_t* key, int32_t* pos_io, int32_t n_class, const int64_t* members,
+                               const int64_t* member_off, int32_t batch, int32_t* out, int32_t* out_off) {
+  if (!key || !pos_io || n_class < 0 || !member_off || !out || !out_off || batch < 0 || *pos_io < 0 || *pos_io > 624)
+    return GS_EINVAL;
+  NpStream rng(key, *pos_io);
+  std::vector<int64_t> x;
+  int32_t w = 0;
+  out_off[0] = 0;
+  for (int c = 0; c < n_class; ++c) {
+    const int64_t n = member_off[c + 1] - member_off[c];
+    if (n < 0 || (n > 0 && !members) || n > 0xffffffffLL) return GS_EINVAL;
+    x.assign(members + member_off[c], members + member_off[c] + n);
+    int64_t* xp = x.data();
+    uint64_t mask = 0;                                   // smallest 2^k - 1 >= i, kept up to date as i falls
+    if (n > 1) {
+      mask = (uint64_t)(n - 1);
+      mask |= mask >> 1;
+      mask |= mask >> 2;
+      mask |= mask >> 4;
+      mask |= mask >> 8;
+      mask |= mask >> 16;
+      mask |= mask >> 32;
+    }
+    for (int64_t i = n - 1; i >= 1; --i) {
+      if ((uint64_t)i <= (mask >> 1)) mask >>= 1;
+      uint64_t j;
+      do {
+        j = (uint64_t)rng.next32() & mask;
+      } while (j > (uint64_t)i);
+      const int64_t t = xp[i];
+      xp[i] = xp[j];
+      xp[j] = t;
+    }
+    const int64_t take = n < batch ? n : batch;
+    for (int64_t i = 0; i < take; ++i) {
+      if (xp[i] < 0 || xp[i] > 0x7fffffffLL) return GS_EINVAL;
+      out[w++] = (int32_t)xp[i];
+    }
+    out_off[c + 1] = w;
+  }
+  *pos_io = rng.pos;
+  return GS_OK;
+}
+
 }  // extern "C"

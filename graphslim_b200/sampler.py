@@ -31,6 +31,34 @@ def fanouts(dataset, nlayers):
     raise ValueError(f"nlayers={nlayers} has no fan-out schedule in the reference")
 
 
+def draw_class_batches(lib, members, batch, out_dtype, cache):
+    """``np.random.permutation(members of class c)[:batch]`` for every class in order (dataset/loader.py:222) on numpy's
+    global legacy generator -- drawn by ``gs_np_legacy_class_batches`` (csrc/host_sampler.cpp: the frozen legacy stream
+    restated, bit-exact incl. the generator position; tests/test_sampler_draws.py), because numpy's own shuffle keeps the
+    interpreter lock busy for ~2 ms per outer step at the Reddit shape and the thread issuing the kernels then waits for
+    it.  Returns (concatenated batches, offsets) like the numpy formulation did."""
+    if "cat" not in cache:
+        off = np.zeros(len(members) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([m.size for m in members])
+        cache["off"] = off
+        cache["cat"] = (np.ascontiguousarray(np.concatenate(members), dtype=np.int64) if off[-1]
+                        else np.zeros(1, dtype=np.int64))
+        cache["cap"] = int(sum(min(int(m.size), int(batch)) for m in members))
+    state = np.random.get_state()
+    if state[0] != "MT19937":
+        raise RuntimeError("numpy's global generator is not the legacy MT19937 stream")
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = np.array([int(state[2])], dtype=np.int32)
+    out = np.empty(max(cache["cap"], 1), dtype=np.int32)
+    out_off = np.zeros(len(members) + 1, dtype=np.int32)
+    rc = lib.gs_np_legacy_class_batches(key.ctypes.data, pos.ctypes.data, len(members), cache["cat"].ctypes.data,
+                                        cache["off"].ctypes.data, int(batch), out.ctypes.data, out_off.ctypes.data)
+    if rc != 0:
+        raise _lib.GraphSlimLibraryError(f"gs_np_legacy_class_batches failed ({rc})")
+    np.random.set_state((state[0], key, int(pos[0]), state[3], state[4]))
+    return out[:out_off[-1]].astype(out_dtype, copy=False), out_off.astype(out_dtype, copy=False)
+
+
 class _TorchMt:
     def __enter__(self):
         raw = torch.get_rng_state().numpy().copy()
@@ -182,10 +210,7 @@ class ClassSampler(_Unpack):
 
     def draw_batches(self):
         """np.random.permutation(class members)[:256] per class, in class order (loader.py:222)."""
-        parts = [np.random.permutation(m)[:self.batch].astype(np.int64) for m in self.members]
-        off = np.zeros(self.n_class + 1, dtype=np.int64)
-        off[1:] = np.cumsum([p.size for p in parts])
-        return np.concatenate(parts), off
+        return draw_class_batches(self.lib, self.members, self.batch, np.int64, self.__dict__.setdefault("_draw", {}))
 
     def begin_host(self, materialise=None):
         """Stage 1 (owns numpy's and torch's global generators): class batches + the serial hops.  Returns a job."""
@@ -407,10 +432,7 @@ class DeviceClassSampler(_Unpack):
     # ---- random streams --------------------------------------------------------------------------
     def draw_batches(self):
         """np.random.permutation(class members)[:256] per class, in class order (loader.py:222)."""
-        parts = [np.random.permutation(m)[:self.batch].astype(np.int32) for m in self.members]
-        off = np.zeros(self.n_class + 1, dtype=np.int32)
-        off[1:] = np.cumsum([p.size for p in parts])
-        return np.concatenate(parts), off
+        return draw_class_batches(self.lib, self.members, self.batch, np.int32, self.__dict__.setdefault("_draw", {}))
 
     def checkout_rng(self):
         """torch's CPU generator -> device.  Nothing may draw from it until `checkin_rng`."""

@@ -343,6 +343,12 @@ int gs_axpby_f32(int64_t n, float a, const float* x, float b, float* y, void* st
 /* ---- host side: bit-exact class / neighbour selection (dataset/loader.py:187-224) ------------
  * One call samples the blocks of every class of one outer step, drawing from an mt19937 state in the
  * layout of torch's CPU generator so the random stream interleaves exactly like the reference's.  */
+/* `np.random.permutation(members of class c)[:batch]` for every class in order (graphslim/dataset/loader.py:222) on
+ * numpy's legacy MT19937 stream: `key` (624 words) and `pos` are np.random.get_state()[1:3] and are advanced in place
+ * (hand them back with np.random.set_state).  members: concatenated int64 ids, member_off: n_class + 1 offsets;
+ * out: int32 batches back to back, out_off: n_class + 1 offsets.  Host only; runs without the interpreter lock. */
+int gs_np_legacy_class_batches(uint32_t* key, int32_t* pos_io, int32_t n_class, const int64_t* members,
+                               const int64_t* member_off, int32_t batch, int32_t* out, int32_t* out_off);
 typedef struct gs_sampler gs_sampler;
 gs_sampler* gs_sampler_create(int32_t n_nodes, const int64_t* rowptr, const int32_t* col, const float* val,
                               int32_t n_hops, const int32_t* fanout);
